@@ -1,0 +1,212 @@
+/* peritext_b200.h — C-ABI of the B200 batch CRDT-merge engine (libperitext_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of inkandswitch/peritext: replaying op logs and flattening the
+ * documents to formatted spans, i.e. what the reference does in
+ *     Micromerge.applyChange -> applyOp          (reference src/micromerge.ts:499-608)
+ *     applyListInsert / applyListUpdate           (src/micromerge.ts:614-724)
+ *     applyAddRemoveMark                          (src/peritext.ts:154-249)
+ *     getTextWithFormatting / addCharactersToSpans(src/peritext.ts:337-455)
+ * for MANY (document, replica) op logs at once.  The reference has no FFI seam (it is pure TypeScript);
+ * these entry points are what an N-API addon behind a `Micromerge` facade binds.
+ *
+ * Conventions: plain C types only, no C++/torch types; every function returns a pt_status code (never
+ * throws); device work is enqueued on the CUDA stream handle given at create time; host buffers passed
+ * in are owned by the caller and may be freed as soon as the call returns.
+ */
+#ifndef PERITEXT_B200_H
+#define PERITEXT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed op records (host and device layout are identical; little endian).
+ *
+ * One LOG = the ops one replica applied to one text list, in that replica's arrival order
+ * (the concatenation of `change.ops` over its applyChange calls, src/micromerge.ts:513).
+ * opIds "ctr@actor" (src/micromerge.ts:488) are packed as (ctr, actor_rank) where actor_rank is the rank
+ * of the actorId among the log's actors in JS string order (UTF-16 code units), so that
+ * compareOpIds (src/micromerge.ts:812-827) == compare (ctr, actor_rank) lexicographically.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Insert (`action:"set", insert:true`, src/micromerge.ts:150-160) or delete (`action:"del"`, :162-168). 16 B. */
+typedef struct pt_insdel_rec {
+    uint32_t ctr;       /* opId counter (>=1)                                                     */
+    uint32_t ref_ctr;   /* insert: reference elemId counter, 0 = HEAD; delete: target elemId ctr */
+    uint16_t actor;     /* opId actor rank                                                        */
+    uint16_t ref_actor; /* reference / target elemId actor rank                                   */
+    uint32_t payload;   /* bits31:30 kind (PT_KIND_*); insert: bit29 = value-pool flag, bits28:0 =
+                           Unicode code point (single-character value) or value-pool index        */
+} pt_insdel_rec;
+
+#define PT_KIND_INSERT 0u
+#define PT_KIND_DELETE 1u
+#define PT_PAYLOAD_KIND(p) ((uint32_t)(p) >> 30)
+#define PT_PAYLOAD_TOKEN(p) ((uint32_t)(p) & 0x3FFFFFFFu)
+#define PT_TOKEN_POOLED 0x20000000u
+
+/* addMark / removeMark (src/peritext.ts:25-65). 32 B. */
+typedef struct pt_mark_rec {
+    uint32_t ctr;         /* opId counter                                                         */
+    uint16_t actor;       /* opId actor rank                                                      */
+    uint8_t  kind;        /* bit0: 0 addMark, 1 removeMark; bits2:1 mark type (PT_MARK_*)          */
+    uint8_t  bounds;      /* bits1:0 start boundary type, bits3:2 end boundary type (PT_BOUND_*)   */
+    uint32_t start_ctr;   /* start.elemId counter (before/after only)                              */
+    uint32_t end_ctr;     /* end.elemId counter (before/after only)                                */
+    uint16_t start_actor; /* start.elemId actor rank                                               */
+    uint16_t end_actor;   /* end.elemId actor rank                                                 */
+    uint32_t attr;        /* link: interned url id; comment: comment-id rank (JS string order of
+                             the id, per batch); PT_ATTR_NONE otherwise                           */
+    uint32_t arrival;     /* number of ins/del records of this log that arrived before this op   */
+    uint32_t reserved;    /* 0                                                                     */
+} pt_mark_rec;
+
+/* Mark types in ALL_MARKS order (src/schema.ts:125). strong/em: inclusive, single; comment:
+ * non-inclusive, allowMultiple; link: non-inclusive, single (src/schema.ts:45-96). */
+#define PT_MARK_STRONG 0u
+#define PT_MARK_EM 1u
+#define PT_MARK_COMMENT 2u
+#define PT_MARK_LINK 3u
+#define PT_BOUND_BEFORE 0u
+#define PT_BOUND_AFTER 1u
+#define PT_BOUND_START_OF_TEXT 2u
+#define PT_BOUND_END_OF_TEXT 3u
+#define PT_ATTR_NONE 0xFFFFFFFFu
+
+/* Per-log descriptor. 32 B. */
+typedef struct pt_log_desc {
+    uint64_t insdel_off; /* first pt_insdel_rec of the log in the batch's insdel array            */
+    uint64_t mark_off;   /* first pt_mark_rec of the log in the batch's mark array                */
+    uint32_t n_insdel;
+    uint32_t n_mark;
+    uint32_t n_actors;   /* actor ranks are < n_actors                                             */
+    uint32_t max_ctr;    /* every ctr in the log is in [1, max_ctr]                                */
+} pt_log_desc;
+
+/* A host-side batch of logs (SoA). */
+typedef struct pt_packed_ops {
+    uint32_t n_logs;
+    const pt_log_desc* logs;     /* [n_logs]                 */
+    const pt_insdel_rec* insdel; /* [sum n_insdel]           */
+    uint64_t n_insdel_total;
+    const pt_mark_rec* marks;    /* [sum n_mark]             */
+    uint64_t n_mark_total;
+} pt_packed_ops;
+
+/* ------------------------------------------------------------------------------------------------
+ * Results
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Per-log status; each maps to a reference throw site. */
+#define PT_LOG_OK 0u
+#define PT_LOG_ELEM_NOT_FOUND 1u /* "List element not found" src/micromerge.ts:752                 */
+#define PT_LOG_BAD_OPID 2u       /* ctr/actor outside the descriptor's bounds, or duplicate opId   */
+#define PT_LOG_BAD_KIND 3u       /* record kind not insert/delete                                  */
+#define PT_LOG_OVERFLOW 4u       /* an engine capacity (comment pool / scratch) was exceeded       */
+#define PT_LOG_CYCLE 5u          /* reference elemId does not causally precede the insert          */
+
+/* Per-log result header. 32 B. */
+typedef struct pt_log_result {
+    uint32_t status;    /* PT_LOG_*                                                                */
+    uint32_t n_elems;   /* list elements incl. tombstones (metadata.length)                        */
+    uint32_t n_visible; /* visible elements (text.length, src/micromerge.ts:657)                   */
+    uint32_t n_spans;   /* FormatSpanWithText count (src/peritext.ts:361)                          */
+    uint64_t digest[2]; /* 128-bit digest of (text tokens, spans, marks) — convergence check       */
+} pt_log_result;
+
+/* One formatted span (src/peritext.ts:35-38). 16 B. Text of span j = tokens [start_j, start_{j+1}). */
+typedef struct pt_span {
+    uint32_t start;       /* index of the span's first visible element                             */
+    uint32_t flags;       /* bit0 strong, bit1 em, bit2 link present, bit3 `comment` key present;
+                             bits31:8 number of comment ids                                        */
+    uint32_t link_attr;   /* url id if bit2, else PT_ATTR_NONE                                     */
+    uint32_t comment_off; /* first comment id of the span in the comment pool (ascending ids)      */
+} pt_span;
+
+#define PT_SPAN_STRONG 1u
+#define PT_SPAN_EM 2u
+#define PT_SPAN_LINK 4u
+#define PT_SPAN_COMMENT 8u
+#define PT_SPAN_NCOMMENTS(f) ((uint32_t)(f) >> 8)
+
+/* Host view of a merged batch; pointers are engine-owned pinned host memory, valid until the next
+ * pt_batch_upload/pt_batch_destroy on the handle. Log i's tokens start at text_off[i], spans at span_off[i]. */
+typedef struct pt_spans_view {
+    uint32_t n_logs;
+    const pt_log_result* results; /* [n_logs]                                                      */
+    const uint64_t* text_off;     /* [n_logs]                                                      */
+    const uint64_t* span_off;     /* [n_logs]                                                      */
+    const uint32_t* text;         /* visible element value tokens (PT_PAYLOAD_TOKEN)               */
+    const pt_span* spans;
+    const uint32_t* comment_pool;
+    uint64_t comment_pool_used;
+} pt_spans_view;
+
+/* Engine limits / tuning. Zero-initialise for defaults. */
+typedef struct pt_limits {
+    uint64_t comment_pool_entries; /* 0: 4 x number of comment mark ops in the batch (+slack)     */
+    uint32_t reserved[6];
+} pt_limits;
+
+typedef enum pt_status {
+    PT_OK = 0,
+    PT_ERR_INVALID = 1,   /* bad argument                                                          */
+    PT_ERR_CUDA = 2,      /* CUDA runtime error (see pt_last_error)                                */
+    PT_ERR_NO_DEVICE = 3, /* no usable sm_100 device                                               */
+    PT_ERR_STATE = 4,     /* call out of order (e.g. merge before upload)                          */
+    PT_ERR_NOMEM = 5
+} pt_status;
+
+typedef struct pt_batch pt_batch; /* opaque; one per (GPU, batch); not thread-safe per handle */
+
+/* Create an engine handle on CUDA device `device`; work is enqueued on `cuda_stream`
+ * (a cudaStream_t / CUstream passed as void*, NULL = legacy default stream). */
+int pt_batch_create(int device, const pt_limits* limits, void* cuda_stream, pt_batch** out);
+
+/* Copy a packed batch host -> device (asynchronous on the handle's stream; the host arrays are staged
+ * through engine-owned pinned memory, so the caller may free them on return). Replaces any previous batch.
+ * This is the H2D leg of Micromerge.applyChange's input (src/micromerge.ts:499). */
+int pt_batch_upload(pt_batch*, const pt_packed_ops* host_ops);
+
+/* Adopt a batch that is ALREADY RESIDENT in device memory (pointers are device pointers owned by the
+ * caller, e.g. torch tensors); only the descriptors are read on the host. */
+int pt_batch_adopt_device(pt_batch*, const pt_packed_ops* host_desc_device_arrays);
+
+/* Enqueue the merge: op-log apply + flatten for every log of the batch (the replacement for the
+ * applyOp loop src/micromerge.ts:513 and getTextWithFormatting src/peritext.ts:337). Asynchronous. */
+int pt_batch_merge(pt_batch*);
+
+/* Block until the handle's stream is idle. */
+int pt_batch_sync(pt_batch*);
+
+/* Copy results device -> host (pinned) and return a view. Synchronises the stream. */
+int pt_batch_download(pt_batch*, pt_spans_view* out);
+
+/* Copy only the per-log result headers (status, counts, digest). Synchronises the stream. */
+int pt_batch_download_results(pt_batch*, pt_log_result* out, uint32_t n_logs);
+
+/* Device pointer to the per-log result headers ([n_logs] pt_log_result) — for the multi-GPU digest
+ * all-gather without a host round trip. */
+int pt_batch_device_results(pt_batch*, void** dev_ptr, uint32_t* n_logs);
+
+/* Number of kernel launches the handle has enqueued so far (bench `gpu_launches`). */
+uint64_t pt_batch_launch_count(const pt_batch*);
+
+/* Time of the last pt_batch_merge on the device, in milliseconds (CUDA events recorded on the
+ * handle's stream around the launches); <0 if not available. Synchronises. */
+float pt_batch_last_merge_ms(pt_batch*);
+
+void pt_batch_destroy(pt_batch*);
+
+const char* pt_strerror(int status);
+const char* pt_last_error(void); /* thread-local detail string of the last failing call */
+const char* pt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERITEXT_B200_H */
