@@ -133,3 +133,97 @@ def run_concurrent(Micromerge, kat, record=None):
     if record is not None:
         record.extend(log)
     return docs, [p1, p2]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Seeded fuzz sessions in the shape of reference test/fuzz.ts:23-199 (driven through any Micromerge class).
+# Deviations: seeded RNG; removeMark really emits removeMark (fuzz.ts:80 emits addMark);
+# removeMark/comment reuses an id the acting replica has already seen, so no concurrent add/remove of one id (Q4).
+# ------------------------------------------------------------------------------------------------------------------
+import random as _random
+
+_URLS = [f"{c}.com" for c in "ABCDEFGHIJKLMNOPQRSTUVWXYZ"]
+_MARKS = ["strong", "em", "link", "comment"]
+
+
+def fuzz_session(Micromerge, seed, n_steps, replicas=3, initial="ABCDE", sync_prob=1.0, full_sync_at_end=True,
+                 max_chars=2, zero_width_prob=0.0):
+    """Returns (docs, logs, queues): logs[r] = Changes replica r applied (own + remote) in arrival order."""
+    rng = _random.Random(seed)
+    docs, _, init = generateDocs(Micromerge, initial, replicas)
+    ids = [d.actorId for d in docs]
+    queues = {a: [] for a in ids}
+    queues[ids[0]].append(init)
+    logs = [[init] for _ in docs]
+    seen_comments = [[] for _ in docs]   # comment ids each replica has seen (own adds + synced)
+    comment_owner = {}
+    n_comment = 0
+
+    def sync(li, ri):
+        for src, dst in ((li, ri), (ri, li)):
+            missing = getMissingChanges(docs[src], docs[dst], queues)
+            pending = list(missing)
+            it = 0
+            while pending:
+                ch = pending.pop(0)
+                try:
+                    docs[dst].applyChange(ch)
+                    logs[dst].append(ch)
+                    for op in ch["ops"]:
+                        if op["action"] == "addMark" and op.get("markType") == "comment":
+                            seen_comments[dst].append(op["attrs"]["id"])
+                except Exception:
+                    pending.append(ch)
+                it += 1
+                assert it < 10000
+
+    for _ in range(n_steps):
+        t = rng.randrange(replicas)
+        doc = docs[t]
+        length = len(doc.root["text"])
+        kind = rng.choice(["insert", "remove", "addMark", "removeMark"])
+        op = None
+        if kind == "insert" or length == 0:
+            index = rng.randrange(length) if length else 0
+            nchars = rng.randrange(max_chars) if length else 1     # fuzz.ts:111-113: randomBytes(n).toString("hex")
+            vals = [rng.choice("0123456789abcdef") for _ in range(2 * nchars)]
+            op = {"path": ["text"], "action": "insert", "index": index, "values": vals}
+        elif kind == "remove":
+            index = rng.randrange(length) + 1
+            count = -(-rng.random() * (length - index) // 1)
+            count = int(count)
+            op = {"path": ["text"], "action": "delete", "index": index, "count": count}
+        else:
+            start = rng.randrange(length)
+            end = start + rng.randrange(length - start) + 1
+            mt = rng.choice(_MARKS)
+            if zero_width_prob and rng.random() < zero_width_prob and not (start == 0 and mt in ("link", "comment")):
+                end = start   # (a zero-width non-inclusive mark at index 0 throws in the reference: getListElementId(-1))
+            op = {"path": ["text"], "action": kind, "startIndex": start, "endIndex": end, "markType": mt}
+            if mt == "link" and kind == "addMark":
+                op["attrs"] = {"url": rng.choice(_URLS)}
+            elif mt == "comment":
+                if kind == "addMark":
+                    n_comment += 1
+                    cid = "comment-%04x-%d" % (rng.randrange(65536), n_comment)
+                    op["attrs"] = {"id": cid}
+                    seen_comments[t].append(cid)
+                else:
+                    if not seen_comments[t]:
+                        continue
+                    op["attrs"] = {"id": rng.choice(seen_comments[t])}
+        r = doc.change([op])
+        queues[ids[t]].append(r["change"])
+        logs[t].append(r["change"])
+        if rng.random() < sync_prob:
+            li = rng.randrange(replicas)
+            ri = rng.randrange(replicas)
+            while ri == li:
+                ri = rng.randrange(replicas)
+            sync(li, ri)
+    if full_sync_at_end:
+        for _ in range(2):
+            for a in range(replicas):
+                for b in range(a + 1, replicas):
+                    sync(a, b)
+    return docs, logs, queues
