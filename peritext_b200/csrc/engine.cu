@@ -1,0 +1,382 @@
+// engine.cu — C-ABI of the batch CRDT-merge engine (include/peritext_b200.h) over the sm_100a kernels.
+//
+// Host responsibilities (all per batch, none per op): size the output regions from the descriptors, bin the logs
+// by size (block size + shared-memory budget per bin), order each bin largest-first for the persistent-CTA work
+// queue, launch, and move results.  There is NO CPU fallback: without a CUDA device every entry point fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "merge_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define PT_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            g_last_error = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return PT_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return PT_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { g_last_error = std::string("cudaMalloc: ") + cudaGetErrorString(e); return PT_ERR_NOMEM; }
+        cap = want; return PT_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct HostBuf {   // pinned
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return PT_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { g_last_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return PT_ERR_NOMEM; }
+        cap = want; return PT_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+constexpr int kNumBins = 4;
+struct BinCfg { uint32_t max_recs; int block; uint32_t smem; int ctas_per_sm; };
+// shared memory per SM: 228 KB, 1 KB reserved per resident CTA, 227 KB max per CTA
+const BinCfg kBins[kNumBins] = {
+    {1536u, 128, 31u * 1024u, 7},
+    {4096u, 256, 74u * 1024u, 3},
+    {6144u, 512, 112u * 1024u, 2},
+    {0xFFFFFFFFu, 1024, 226u * 1024u, 1},
+};
+
+inline size_t al16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+// Worst-case arena bytes of one log: mirrors every Arena::alloc in merge_one_log with M <= N <= n,
+// S <= 2m+2, nvis <= n, Mc <= m, nspans <= 2m+1.
+size_t arena_worst_bytes(uint64_t n, uint64_t m, uint64_t KS) {
+    const size_t I = (n < 32000 && m < 32000) ? 2 : 4;
+    size_t b = 0;
+    auto A = [&](uint64_t count, size_t sz) { b += al16((size_t)count * sz); };
+    A(KS, I); A(n, I); A(n, I); A(n + 1, I); A(n + 1, 1); A(n, 1);                 // T Par RunOrPos AnyChild Multi Del
+    A(n + 1, I); A(n + 1, I);                                                      // RunHead RunTail
+    A(n + 1, I); A(n + 1, 4); A(n + 2, 4); A(n + 2, I); A(n + 1, I); A(n + 1, I); A(n + 1, I); A(n + 2, 4);  // D
+    for (int k = 0; k < 4; k++) A(2 * n + 3, I);                                   // Euler
+    const uint64_t NW = n / 32 + 2;
+    A(n + 1, 1); A(NW + 1, 4); A(NW + 1, I);                                       // SeqDel VisBits VisPre
+    if (m) {
+        const uint64_t KW = KS / 32 + 2, S = 2 * m + 2, Mc = m, nsp = 2 * m + 1;
+        A(KW + 1, 4); A(KW + 1, I); for (int k = 0; k < 4; k++) A(m + 1, I);       // KBits KPre ByRank MRank IvA IvB
+        A(n + 2, 1); A(NW + 1, 4); A(NW + 1, I);                                   // Bnd BndBits SegPre
+        A(2 * S + 2, 4); A(S + 1, 4); A(S + 1, 4); A(S + 2, 4); A(m + 1, 4);       // Tree SegFlags SegLink CDiff CompactC
+        A(n / 32 + 3, 4); A(2 * Mc + 1, 4); A(2 * Mc + 1, I); A(2 * Mc + 1, I);    // CHead PcId PcA PcB
+        A(n + 1, I); A(NW + 1, 4); A(NW + 1, I);                                   // VisSeg HeadBits HeadPre
+        A(nsp + 1, 4); A(nsp + 1, 4); A(nsp + 1, 4);                               // SpanCC SpanCO SpanCur
+    }
+    return b + 256;
+}
+
+}  // namespace
+
+struct pt_batch {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    pt_limits limits{};
+    // batch
+    bool have_batch = false, merged = false, adopted = false;
+    uint32_t n_logs = 0;
+    uint64_t n_insdel = 0, n_mark = 0, n_text = 0, n_span = 0, pool_cap = 0;
+    std::vector<pt_log_desc> h_desc;
+    std::vector<uint64_t> h_text_off, h_span_off;
+    std::vector<uint32_t> h_order;
+    uint32_t bin_first[kNumBins + 1] = {0};
+    size_t bin_slab[kNumBins] = {0};
+    // device
+    DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_pool_used, d_slab;
+    const pt_insdel_rec* dp_insdel = nullptr;
+    const pt_mark_rec* dp_marks = nullptr;
+    // pinned host
+    HostBuf h_stage, h_results, h_text, h_spans, h_pool, h_misc;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    uint64_t pool_used_host = 0;
+};
+
+namespace {
+
+int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
+    b->n_logs = ops->n_logs;
+    b->n_insdel = ops->n_insdel_total;
+    b->n_mark = ops->n_mark_total;
+    b->h_desc.assign(ops->logs, ops->logs + ops->n_logs);
+    b->h_text_off.resize(b->n_logs); b->h_span_off.resize(b->n_logs);
+    uint64_t to = 0, so = 0, ncomment_bound = 0;
+    std::vector<uint32_t> bins[kNumBins];
+    for (int k = 0; k < kNumBins; k++) b->bin_slab[k] = 0;
+    for (uint32_t i = 0; i < b->n_logs; i++) {
+        const pt_log_desc& L = b->h_desc[i];
+        if (L.insdel_off + L.n_insdel > b->n_insdel || L.mark_off + L.n_mark > b->n_mark) { g_last_error = "log descriptor out of range"; return PT_ERR_INVALID; }
+        b->h_text_off[i] = to; b->h_span_off[i] = so;
+        to += L.n_insdel;
+        so += std::min<uint64_t>(L.n_insdel, 2ull * L.n_mark + 1);
+        ncomment_bound += L.n_mark;
+        uint64_t recs = (uint64_t)L.n_insdel + L.n_mark;
+        int bin = 0; while (recs > kBins[bin].max_recs) bin++;
+        bins[bin].push_back(i);
+        uint64_t KS = (uint64_t)L.max_ctr * (L.n_actors ? L.n_actors : 1);
+        if (KS > 0x7FFFFFFFull) { g_last_error = "max_ctr * n_actors too large; re-rank counters densely on the host"; return PT_ERR_INVALID; }
+        b->bin_slab[bin] = std::max(b->bin_slab[bin], arena_worst_bytes(L.n_insdel, L.n_mark, KS));
+    }
+    b->n_text = to; b->n_span = so;
+    b->pool_cap = b->limits.comment_pool_entries ? b->limits.comment_pool_entries : 64ull * ncomment_bound + 1024;
+    b->h_order.clear();
+    for (int k = 0; k < kNumBins; k++) {
+        b->bin_first[k] = (uint32_t)b->h_order.size();
+        auto& v = bins[k];
+        std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) {
+            return (uint64_t)b->h_desc[x].n_insdel + b->h_desc[x].n_mark > (uint64_t)b->h_desc[y].n_insdel + b->h_desc[y].n_mark; });
+        b->h_order.insert(b->h_order.end(), v.begin(), v.end());
+    }
+    b->bin_first[kNumBins] = (uint32_t)b->h_order.size();
+    return PT_OK;
+}
+
+int alloc_and_upload_plan(pt_batch* b) {
+    int rc;
+    const size_t n = b->n_logs;
+    if ((rc = b->d_desc.reserve(std::max<size_t>(1, n) * sizeof(pt_log_desc)))) return rc;
+    if ((rc = b->d_order.reserve(std::max<size_t>(1, n) * 4))) return rc;
+    if ((rc = b->d_counters.reserve(kNumBins * 4))) return rc;
+    if ((rc = b->d_results.reserve(std::max<size_t>(1, n) * sizeof(pt_log_result)))) return rc;
+    if ((rc = b->d_text_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
+    if ((rc = b->d_span_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
+    if ((rc = b->d_text.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
+    if ((rc = b->d_spans.reserve(std::max<uint64_t>(1, b->n_span) * sizeof(pt_span)))) return rc;
+    if ((rc = b->d_pool.reserve(std::max<uint64_t>(1, b->pool_cap) * 4))) return rc;
+    if ((rc = b->d_pool_used.reserve(8))) return rc;
+    size_t slab_total = 0;
+    for (int k = 0; k < kNumBins; k++) {
+        uint32_t cnt = b->bin_first[k + 1] - b->bin_first[k];
+        if (!cnt) continue;
+        size_t grid = std::min<size_t>(cnt, (size_t)b->num_sms * kBins[k].ctas_per_sm);
+        slab_total = std::max(slab_total, grid * b->bin_slab[k]);
+    }
+    if ((rc = b->d_slab.reserve(std::max<size_t>(slab_total, 16)))) return rc;
+    // stage the small host-derived arrays through pinned memory
+    size_t stage = n * (sizeof(pt_log_desc) + 4 + 8 + 8) + 64;
+    if ((rc = b->h_stage.reserve(stage))) return rc;
+    char* s = (char*)b->h_stage.p;
+    if (n) {
+        memcpy(s, b->h_desc.data(), n * sizeof(pt_log_desc));
+        PT_CUDA(cudaMemcpyAsync(b->d_desc.p, s, n * sizeof(pt_log_desc), cudaMemcpyHostToDevice, b->stream)); s += n * sizeof(pt_log_desc);
+        memcpy(s, b->h_order.data(), n * 4);
+        PT_CUDA(cudaMemcpyAsync(b->d_order.p, s, n * 4, cudaMemcpyHostToDevice, b->stream)); s += n * 4;
+        memcpy(s, b->h_text_off.data(), n * 8);
+        PT_CUDA(cudaMemcpyAsync(b->d_text_off.p, s, n * 8, cudaMemcpyHostToDevice, b->stream)); s += n * 8;
+        memcpy(s, b->h_span_off.data(), n * 8);
+        PT_CUDA(cudaMemcpyAsync(b->d_span_off.p, s, n * 8, cudaMemcpyHostToDevice, b->stream)); s += n * 8;
+    }
+    return PT_OK;
+}
+
+template <int BLOCK>
+int launch_bin(pt_batch* b, int k, ptk::BatchParams P) {
+    uint32_t cnt = b->bin_first[k + 1] - b->bin_first[k];
+    if (!cnt) return PT_OK;
+    uint32_t grid = (uint32_t)std::min<size_t>(cnt, (size_t)b->num_sms * kBins[k].ctas_per_sm);
+    P.order = (const uint32_t*)b->d_order.p + b->bin_first[k];
+    P.n_work = cnt;
+    P.work_counter = (uint32_t*)b->d_counters.p + k;
+    P.slab_bytes = b->bin_slab[k];
+    P.smem_arena_bytes = kBins[k].smem;
+    PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_kernel<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBins[k].smem));
+    ptk::merge_logs_kernel<BLOCK><<<grid, BLOCK, kBins[k].smem, b->stream>>>(P);
+    PT_CUDA(cudaGetLastError());
+    b->launches++;
+    return PT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pt_batch_create(int device, const pt_limits* limits, void* cuda_stream, pt_batch** out) {
+    if (!out) return PT_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        g_last_error = e != cudaSuccess ? cudaGetErrorString(e) : "no such CUDA device (this engine has no CPU fallback)";
+        return PT_ERR_NO_DEVICE;
+    }
+    PT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { g_last_error = "device is not sm_100-class (kernels are built for sm_100a only)"; return PT_ERR_NO_DEVICE; }
+    pt_batch* b = new pt_batch();
+    b->device = device; b->stream = (cudaStream_t)cuda_stream; b->num_sms = prop.multiProcessorCount;
+    if (limits) b->limits = *limits;
+    if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) { delete b; g_last_error = "cudaEventCreate failed"; return PT_ERR_CUDA; }
+    *out = b;
+    return PT_OK;
+}
+
+static int upload_common(pt_batch* b, const pt_packed_ops* ops, bool adopt) {
+    if (!b || !ops || (ops->n_logs && !ops->logs)) return PT_ERR_INVALID;
+    PT_CUDA(cudaSetDevice(b->device));
+    b->have_batch = false; b->merged = false;
+    int rc = plan_batch(b, ops);
+    if (rc) return rc;
+    if ((rc = alloc_and_upload_plan(b))) return rc;
+    if (adopt) {
+        b->dp_insdel = ops->insdel; b->dp_marks = ops->marks; b->adopted = true;
+    } else {
+        if ((rc = b->d_insdel.reserve(std::max<uint64_t>(1, b->n_insdel) * sizeof(pt_insdel_rec)))) return rc;
+        if ((rc = b->d_marks.reserve(std::max<uint64_t>(1, b->n_mark) * sizeof(pt_mark_rec)))) return rc;
+        if (b->n_insdel) PT_CUDA(cudaMemcpyAsync(b->d_insdel.p, ops->insdel, b->n_insdel * sizeof(pt_insdel_rec), cudaMemcpyHostToDevice, b->stream));
+        if (b->n_mark) PT_CUDA(cudaMemcpyAsync(b->d_marks.p, ops->marks, b->n_mark * sizeof(pt_mark_rec), cudaMemcpyHostToDevice, b->stream));
+        b->dp_insdel = (const pt_insdel_rec*)b->d_insdel.p; b->dp_marks = (const pt_mark_rec*)b->d_marks.p; b->adopted = false;
+        // the caller's buffers may be pageable and freed on return: finish the copies now
+        PT_CUDA(cudaStreamSynchronize(b->stream));
+    }
+    b->have_batch = true;
+    return PT_OK;
+}
+
+int pt_batch_upload(pt_batch* b, const pt_packed_ops* ops) { return upload_common(b, ops, false); }
+int pt_batch_adopt_device(pt_batch* b, const pt_packed_ops* ops) { return upload_common(b, ops, true); }
+
+int pt_batch_merge(pt_batch* b) {
+    if (!b) return PT_ERR_INVALID;
+    if (!b->have_batch) { g_last_error = "pt_batch_merge before pt_batch_upload"; return PT_ERR_STATE; }
+    PT_CUDA(cudaSetDevice(b->device));
+    PT_CUDA(cudaEventRecord(b->ev0, b->stream));
+    PT_CUDA(cudaMemsetAsync(b->d_counters.p, 0, kNumBins * 4, b->stream));
+    PT_CUDA(cudaMemsetAsync(b->d_pool_used.p, 0, 8, b->stream));
+    ptk::BatchParams P{};
+    P.desc = (const pt_log_desc*)b->d_desc.p;
+    P.insdel = b->dp_insdel; P.marks = b->dp_marks;
+    P.results = (pt_log_result*)b->d_results.p;
+    P.text_off = (const uint64_t*)b->d_text_off.p; P.span_off = (const uint64_t*)b->d_span_off.p;
+    P.text = (uint32_t*)b->d_text.p; P.spans = (pt_span*)b->d_spans.p;
+    P.comment_pool = (uint32_t*)b->d_pool.p; P.comment_used = (unsigned long long*)b->d_pool_used.p; P.comment_cap = b->pool_cap;
+    P.slab = (char*)b->d_slab.p;
+    int rc;
+    // largest logs first: the long-running CTAs start earliest
+    if ((rc = launch_bin<1024>(b, 3, P))) return rc;
+    if ((rc = launch_bin<512>(b, 2, P))) return rc;
+    if ((rc = launch_bin<256>(b, 1, P))) return rc;
+    if ((rc = launch_bin<128>(b, 0, P))) return rc;
+    PT_CUDA(cudaEventRecord(b->ev1, b->stream));
+    b->merged = true;
+    return PT_OK;
+}
+
+int pt_batch_sync(pt_batch* b) {
+    if (!b) return PT_ERR_INVALID;
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    return PT_OK;
+}
+
+float pt_batch_last_merge_ms(pt_batch* b) {
+    if (!b || !b->merged) return -1.f;
+    if (cudaEventSynchronize(b->ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+int pt_batch_download_results(pt_batch* b, pt_log_result* out, uint32_t n_logs) {
+    if (!b || (!out && n_logs)) return PT_ERR_INVALID;
+    if (!b->merged) { g_last_error = "download before merge"; return PT_ERR_STATE; }
+    if (n_logs > b->n_logs) return PT_ERR_INVALID;
+    int rc;
+    if ((rc = b->h_results.reserve(std::max<size_t>(1, b->n_logs) * sizeof(pt_log_result)))) return rc;
+    if (n_logs) PT_CUDA(cudaMemcpyAsync(b->h_results.p, b->d_results.p, (size_t)n_logs * sizeof(pt_log_result), cudaMemcpyDeviceToHost, b->stream));
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    if (n_logs) memcpy(out, b->h_results.p, (size_t)n_logs * sizeof(pt_log_result));
+    return PT_OK;
+}
+
+int pt_batch_download(pt_batch* b, pt_spans_view* out) {
+    if (!b || !out) return PT_ERR_INVALID;
+    if (!b->merged) { g_last_error = "download before merge"; return PT_ERR_STATE; }
+    int rc;
+    const size_t n = b->n_logs;
+    if ((rc = b->h_results.reserve(std::max<size_t>(1, n) * sizeof(pt_log_result)))) return rc;
+    if ((rc = b->h_text.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
+    if ((rc = b->h_spans.reserve(std::max<uint64_t>(1, b->n_span) * sizeof(pt_span)))) return rc;
+    if ((rc = b->h_misc.reserve(16))) return rc;
+    PT_CUDA(cudaMemcpyAsync(b->h_misc.p, b->d_pool_used.p, 8, cudaMemcpyDeviceToHost, b->stream));
+    if (n) PT_CUDA(cudaMemcpyAsync(b->h_results.p, b->d_results.p, n * sizeof(pt_log_result), cudaMemcpyDeviceToHost, b->stream));
+    if (b->n_text) PT_CUDA(cudaMemcpyAsync(b->h_text.p, b->d_text.p, b->n_text * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (b->n_span) PT_CUDA(cudaMemcpyAsync(b->h_spans.p, b->d_spans.p, b->n_span * sizeof(pt_span), cudaMemcpyDeviceToHost, b->stream));
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    uint64_t used = *(unsigned long long*)b->h_misc.p;
+    if (used > b->pool_cap) used = b->pool_cap;
+    b->pool_used_host = used;
+    if ((rc = b->h_pool.reserve(std::max<uint64_t>(1, used) * 4))) return rc;
+    if (used) {
+        PT_CUDA(cudaMemcpyAsync(b->h_pool.p, b->d_pool.p, used * 4, cudaMemcpyDeviceToHost, b->stream));
+        PT_CUDA(cudaStreamSynchronize(b->stream));
+    }
+    out->n_logs = b->n_logs;
+    out->results = (const pt_log_result*)b->h_results.p;
+    out->text_off = b->h_text_off.data();
+    out->span_off = b->h_span_off.data();
+    out->text = (const uint32_t*)b->h_text.p;
+    out->spans = (const pt_span*)b->h_spans.p;
+    out->comment_pool = (const uint32_t*)b->h_pool.p;
+    out->comment_pool_used = used;
+    return PT_OK;
+}
+
+int pt_batch_device_results(pt_batch* b, void** dev_ptr, uint32_t* n_logs) {
+    if (!b || !dev_ptr) return PT_ERR_INVALID;
+    if (!b->have_batch) return PT_ERR_STATE;
+    *dev_ptr = b->d_results.p;
+    if (n_logs) *n_logs = b->n_logs;
+    return PT_OK;
+}
+
+uint64_t pt_batch_launch_count(const pt_batch* b) { return b ? b->launches : 0; }
+
+void pt_batch_destroy(pt_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
+                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_pool_used, &b->d_slab}) d->release();
+    for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc}) h->release();
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    delete b;
+}
+
+const char* pt_strerror(int status) {
+    switch (status) {
+        case PT_OK: return "ok";
+        case PT_ERR_INVALID: return "invalid argument";
+        case PT_ERR_CUDA: return "CUDA runtime error";
+        case PT_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (no CPU fallback)";
+        case PT_ERR_STATE: return "call out of order";
+        case PT_ERR_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+const char* pt_last_error(void) { return g_last_error.c_str(); }
+const char* pt_version(void) { return "peritext_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

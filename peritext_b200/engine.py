@@ -1,0 +1,168 @@
+"""ctypes binding of the engine's C-ABI (include/peritext_b200.h, built as peritext_b200/libperitext_b200.so).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable, every entry point raises
+``EngineError``.  torch is not needed here; pass ``torch.cuda.current_stream().cuda_stream`` as ``stream`` to enqueue
+on a torch stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from .packing import (RESULT_DT, SPAN_DT, MergedBatch, PackedBatch)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libperitext_b200.so")
+_lib = None
+
+EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_adopt_device", "pt_batch_merge", "pt_batch_sync",
+           "pt_batch_download", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count",
+           "pt_batch_last_merge_ms", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _PackedOps(ctypes.Structure):
+    _fields_ = [("n_logs", ctypes.c_uint32), ("logs", ctypes.c_void_p), ("insdel", ctypes.c_void_p),
+                ("n_insdel_total", ctypes.c_uint64), ("marks", ctypes.c_void_p), ("n_mark_total", ctypes.c_uint64)]
+
+
+class _SpansView(ctypes.Structure):
+    _fields_ = [("n_logs", ctypes.c_uint32), ("results", ctypes.c_void_p), ("text_off", ctypes.c_void_p),
+                ("span_off", ctypes.c_void_p), ("text", ctypes.c_void_p), ("spans", ctypes.c_void_p),
+                ("comment_pool", ctypes.c_void_p), ("comment_pool_used", ctypes.c_uint64)]
+
+
+class _Limits(ctypes.Structure):
+    _fields_ = [("comment_pool_entries", ctypes.c_uint64), ("reserved", ctypes.c_uint32 * 6)]
+
+
+def load_library() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          f"(make -C peritext_b200/csrc). There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
+    L.pt_batch_create.argtypes = [ctypes.c_int, vp, vp, ctypes.POINTER(vp)]
+    L.pt_batch_upload.argtypes = [vp, vp]
+    L.pt_batch_adopt_device.argtypes = [vp, vp]
+    L.pt_batch_merge.argtypes = [vp]
+    L.pt_batch_sync.argtypes = [vp]
+    L.pt_batch_download.argtypes = [vp, vp]
+    L.pt_batch_download_results.argtypes = [vp, vp, u32]
+    L.pt_batch_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u32)]
+    L.pt_batch_launch_count.argtypes = [vp]; L.pt_batch_launch_count.restype = u64
+    L.pt_batch_last_merge_ms.argtypes = [vp]; L.pt_batch_last_merge_ms.restype = ctypes.c_float
+    L.pt_batch_destroy.argtypes = [vp]; L.pt_batch_destroy.restype = None
+    L.pt_strerror.argtypes = [ctypes.c_int]; L.pt_strerror.restype = ctypes.c_char_p
+    L.pt_last_error.restype = ctypes.c_char_p
+    L.pt_version.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        L = load_library()
+        raise EngineError(f"{what}: {L.pt_strerror(rc).decode()} ({L.pt_last_error().decode()})")
+
+
+class BatchEngine:
+    """One handle per (GPU, batch).  ``upload`` -> ``merge`` -> ``download``."""
+
+    def __init__(self, device: int = 0, stream: int | None = None, comment_pool_entries: int = 0):
+        L = load_library()
+        self._L = L
+        self._h = ctypes.c_void_p()
+        lim = _Limits(comment_pool_entries, (ctypes.c_uint32 * 6)())
+        _check(L.pt_batch_create(device, ctypes.byref(lim), ctypes.c_void_p(stream or 0), ctypes.byref(self._h)), "pt_batch_create")
+        self._keep = None
+        self.n_logs = 0
+
+    def _ops_struct(self, desc, insdel_ptr, n_insdel, marks_ptr, n_mark):
+        return _PackedOps(len(desc), desc.ctypes.data, insdel_ptr, n_insdel, marks_ptr, n_mark)
+
+    def upload(self, batch: PackedBatch):
+        desc = np.ascontiguousarray(batch.desc)
+        insdel = np.ascontiguousarray(batch.insdel)
+        marks = np.ascontiguousarray(batch.marks)
+        ops = self._ops_struct(desc, insdel.ctypes.data, len(insdel), marks.ctypes.data, len(marks))
+        _check(self._L.pt_batch_upload(self._h, ctypes.byref(ops)), "pt_batch_upload")
+        self.n_logs = len(desc)
+
+    def adopt_device(self, desc: np.ndarray, insdel_dev_ptr: int, n_insdel: int, marks_dev_ptr: int, n_mark: int):
+        """Use op arrays already resident in device memory (e.g. ``tensor.data_ptr()``); caller keeps them alive."""
+        desc = np.ascontiguousarray(desc)
+        ops = self._ops_struct(desc, insdel_dev_ptr, n_insdel, marks_dev_ptr, n_mark)
+        _check(self._L.pt_batch_adopt_device(self._h, ctypes.byref(ops)), "pt_batch_adopt_device")
+        self.n_logs = len(desc)
+
+    def merge(self):
+        _check(self._L.pt_batch_merge(self._h), "pt_batch_merge")
+
+    def sync(self):
+        _check(self._L.pt_batch_sync(self._h), "pt_batch_sync")
+
+    @property
+    def last_merge_ms(self) -> float:
+        return float(self._L.pt_batch_last_merge_ms(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.pt_batch_launch_count(self._h))
+
+    def device_results_ptr(self) -> int:
+        p = ctypes.c_void_p(); n = ctypes.c_uint32()
+        _check(self._L.pt_batch_device_results(self._h, ctypes.byref(p), ctypes.byref(n)), "pt_batch_device_results")
+        return int(p.value or 0)
+
+    def results(self) -> np.ndarray:
+        out = np.zeros(self.n_logs, RESULT_DT)
+        _check(self._L.pt_batch_download_results(self._h, out.ctypes.data, self.n_logs), "pt_batch_download_results")
+        return out
+
+    def download(self, copy: bool = True) -> MergedBatch:
+        v = _SpansView()
+        _check(self._L.pt_batch_download(self._h, ctypes.byref(v)), "pt_batch_download")
+        n = v.n_logs
+
+        def arr(ptr, count, dt):
+            if not count:
+                return np.zeros(0, dt)
+            buf = (ctypes.c_char * (count * np.dtype(dt).itemsize)).from_address(ptr)
+            a = np.frombuffer(buf, dtype=dt, count=count)
+            return a.copy() if copy else a
+
+        results = arr(v.results, n, RESULT_DT)
+        text_off = arr(v.text_off, n, np.uint64)
+        span_off = arr(v.span_off, n, np.uint64)
+        n_text = int(text_off[-1]) + 0 if n else 0
+        # capacities: the last log's region ends at its offset + its counts
+        if n:
+            n_text = int(text_off[-1]) + int(results[-1]["n_visible"])
+            n_span = int(span_off[-1]) + int(results[-1]["n_spans"])
+        else:
+            n_span = 0
+        return MergedBatch(results, text_off, span_off, arr(v.text, n_text, np.uint32), arr(v.spans, n_span, SPAN_DT),
+                           arr(v.comment_pool, int(v.comment_pool_used), np.uint32))
+
+    def run(self, batch: PackedBatch) -> MergedBatch:
+        self.upload(batch); self.merge(); return self.download()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.pt_batch_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
