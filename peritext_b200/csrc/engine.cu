@@ -248,8 +248,13 @@ static int upload_common(pt_batch* b, const pt_packed_ops* ops, bool adopt) {
         if (b->n_insdel) PT_CUDA(cudaMemcpyAsync(b->d_insdel.p, ops->insdel, b->n_insdel * sizeof(pt_insdel_rec), cudaMemcpyHostToDevice, b->stream));
         if (b->n_mark) PT_CUDA(cudaMemcpyAsync(b->d_marks.p, ops->marks, b->n_mark * sizeof(pt_mark_rec), cudaMemcpyHostToDevice, b->stream));
         b->dp_insdel = (const pt_insdel_rec*)b->d_insdel.p; b->dp_marks = (const pt_mark_rec*)b->d_marks.p; b->adopted = false;
-        // the caller's buffers may be pageable and freed on return: finish the copies now
-        PT_CUDA(cudaStreamSynchronize(b->stream));
+        // pageable caller buffers may be freed on return: finish the copies now (pinned ones stay asynchronous)
+        auto pinned = [](const void* p) {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+            return a.type == cudaMemoryTypeHost;
+        };
+        if (!((b->n_insdel == 0 || pinned(ops->insdel)) && (b->n_mark == 0 || pinned(ops->marks)))) PT_CUDA(cudaStreamSynchronize(b->stream));
     }
     b->have_batch = true;
     return PT_OK;
