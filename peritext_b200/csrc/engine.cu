@@ -5,6 +5,7 @@
 // queue, launch, and move results.  There is NO CPU fallback: without a CUDA device every entry point fails.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -54,7 +55,7 @@ struct HostBuf {   // pinned
 constexpr int kNumBins = 4;
 struct BinCfg { uint32_t max_recs; int block; uint32_t smem; int ctas_per_sm; };
 // shared memory per SM: 228 KB, 1 KB reserved per resident CTA, 227 KB max per CTA
-const BinCfg kBins[kNumBins] = {
+BinCfg kBins[kNumBins] = {
     {1536u, 128, 31u * 1024u, 7},
     {4096u, 256, 74u * 1024u, 3},
     {6144u, 512, 112u * 1024u, 2},
@@ -63,25 +64,25 @@ const BinCfg kBins[kNumBins] = {
 
 inline size_t al16(size_t b) { return (b + 15) & ~(size_t)15; }
 
-// Worst-case arena bytes of one log: mirrors every Arena::alloc in merge_one_log with M <= N <= n,
-// S <= 2m+2, nvis <= n, Mc <= m, nspans <= 2m+1.
+// Worst-case arena bytes of one log: an upper bound on the sum of every Arena::alloc in merge_one_log with
+// M <= N <= n, S <= 2m+2, nvis <= n, Mc <= m, nspans <= 2m+1 (released arrays are counted too).
 size_t arena_worst_bytes(uint64_t n, uint64_t m, uint64_t KS) {
     const size_t I = (n < 32000 && m < 32000) ? 2 : 4;
     size_t b = 0;
     auto A = [&](uint64_t count, size_t sz) { b += al16((size_t)count * sz); };
-    A(KS, I); A(n, I); A(n, I); A(n + 1, I); A(n + 1, 1); A(n, 1);                 // T Par RunOrPos AnyChild Multi Del
-    A(n + 1, I); A(n + 1, I);                                                      // RunHead RunTail
-    A(n + 1, I); A(n + 1, 4); A(n + 2, 4); A(n + 2, I); A(n + 1, I); A(n + 1, I); A(n + 1, I); A(n + 2, 4);  // D
-    for (int k = 0; k < 4; k++) A(2 * n + 3, I);                                   // Euler
-    const uint64_t NW = n / 32 + 2;
-    A(n + 1, 1); A(NW + 1, 4); A(NW + 1, I);                                       // SeqDel VisBits VisPre
+    const uint64_t NWr = (n + 31) / 32 + 1;
+    A(KS, I); A(NWr, 4); A(NWr, 4); A(NWr, 4); A(NWr, I); A(NWr, I);               // T InsBits HeadBits VisBits HeadPre VisPre
+    A(NWr * 32 + 32, 1); A(NWr * 32 + 32, 1);                                      // Other Del
+    A(2 * n + 3, 8);                                                               // Node
+    A(n + 1, I); A(n + 2, 4); A(n + 2, 4); A(n + 1, I); A(n + 1, 4); A(n + 2, I);  // RunHead PosBase VisBase Prun Key GrpOff
+    A(n + 1, I); A(n + 1, I); A(n + 1, I);                                         // Unsorted Sorted SPos
     if (m) {
-        const uint64_t KW = KS / 32 + 2, S = 2 * m + 2, Mc = m, nsp = 2 * m + 1;
-        A(KW + 1, 4); A(KW + 1, I); for (int k = 0; k < 4; k++) A(m + 1, I);       // KBits KPre ByRank MRank IvA IvB
-        A(n + 2, 1); A(NW + 1, 4); A(NW + 1, I);                                   // Bnd BndBits SegPre
+        const uint64_t KW = KS / 32 + 2, S = 2 * m + 2, Mc = m, nsp = 2 * m + 1, NWp = (n + 32) / 32 + 1;
+        A(KW + 1, 4); A(KW + 1, I); for (int k = 0; k < 6; k++) A(m + 1, I);       // KBits KPre ByRank MRank IvA IvB IvVA IvVB
+        A(NWp + 1, 4); A(NWp + 1, I);                                              // BndBits SegPre
         A(2 * S + 2, 4); A(S + 1, 4); A(S + 1, 4); A(S + 2, 4); A(m + 1, 4);       // Tree SegFlags SegLink CDiff CompactC
         A(n / 32 + 3, 4); A(2 * Mc + 1, 4); A(2 * Mc + 1, I); A(2 * Mc + 1, I);    // CHead PcId PcA PcB
-        A(n + 1, I); A(NW + 1, 4); A(NW + 1, I);                                   // VisSeg HeadBits HeadPre
+        A(n + 1, I); A(n / 32 + 2, 4); A(n / 32 + 2, I);                           // VisSeg HeadB HeadP
         A(nsp + 1, 4); A(nsp + 1, 4); A(nsp + 1, 4);                               // SpanCC SpanCO SpanCur
     }
     return b + 256;
@@ -116,7 +117,30 @@ struct pt_batch {
 
 namespace {
 
+// PT_BINS="max_recs:block:smem_kb:ctas_per_sm,..." (4 entries, ascending; last max_recs ignored) overrides the bins (tuning)
+void load_bins_from_env() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char* e = getenv("PT_BINS");
+    if (!e) return;
+    BinCfg tmp[kNumBins];
+    int k = 0;
+    const char* p = e;
+    while (k < kNumBins && *p) {
+        unsigned long a, bl, sm, ct; int used = 0;
+        if (sscanf(p, "%lu:%lu:%lu:%lu%n", &a, &bl, &sm, &ct, &used) != 4) return;
+        if (bl != 128 && bl != 256 && bl != 512 && bl != 1024) return;
+        tmp[k++] = BinCfg{(uint32_t)a, (int)bl, (uint32_t)(sm * 1024), (int)ct};
+        p += used; if (*p == ',') p++;
+    }
+    if (k != kNumBins) return;
+    tmp[kNumBins - 1].max_recs = 0xFFFFFFFFu;
+    for (int i = 0; i < kNumBins; i++) kBins[i] = tmp[i];
+}
+
 int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
+    load_bins_from_env();
     b->n_logs = ops->n_logs;
     b->n_insdel = ops->n_insdel_total;
     b->n_mark = ops->n_mark_total;
@@ -192,9 +216,8 @@ int alloc_and_upload_plan(pt_batch* b) {
 }
 
 template <int BLOCK>
-int launch_bin(pt_batch* b, int k, ptk::BatchParams P) {
+int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P) {
     uint32_t cnt = b->bin_first[k + 1] - b->bin_first[k];
-    if (!cnt) return PT_OK;
     uint32_t grid = (uint32_t)std::min<size_t>(cnt, (size_t)b->num_sms * kBins[k].ctas_per_sm);
     P.order = (const uint32_t*)b->d_order.p + b->bin_first[k];
     P.n_work = cnt;
@@ -206,6 +229,15 @@ int launch_bin(pt_batch* b, int k, ptk::BatchParams P) {
     PT_CUDA(cudaGetLastError());
     b->launches++;
     return PT_OK;
+}
+int launch_bin(pt_batch* b, int k, const ptk::BatchParams& P) {
+    if (b->bin_first[k + 1] == b->bin_first[k]) return PT_OK;
+    switch (kBins[k].block) {
+        case 128: return launch_bin_t<128>(b, k, P);
+        case 256: return launch_bin_t<256>(b, k, P);
+        case 512: return launch_bin_t<512>(b, k, P);
+        default: return launch_bin_t<1024>(b, k, P);
+    }
 }
 
 }  // namespace
@@ -280,10 +312,7 @@ int pt_batch_merge(pt_batch* b) {
     P.slab = (char*)b->d_slab.p;
     int rc;
     // largest logs first: the long-running CTAs start earliest
-    if ((rc = launch_bin<1024>(b, 3, P))) return rc;
-    if ((rc = launch_bin<512>(b, 2, P))) return rc;
-    if ((rc = launch_bin<256>(b, 1, P))) return rc;
-    if ((rc = launch_bin<128>(b, 0, P))) return rc;
+    for (int k = kNumBins - 1; k >= 0; k--) if ((rc = launch_bin(b, k, P))) return rc;
     PT_CUDA(cudaEventRecord(b->ev1, b->stream));
     b->merged = true;
     return PT_OK;

@@ -1,4 +1,4 @@
-// merge_kernel.cuh — the op-log apply + flatten kernel (sm_100a).
+// merge_kernel.cuh — the op-log apply + flatten kernel (sm_100a), v2.
 //
 // One CTA materialises one LOG (one replica's op log of one document) end to end:
 //   packed records in HBM  ->  element sequence (RGA order)  ->  visible text + formatted spans + digest in HBM.
@@ -10,6 +10,11 @@
 //  tests/kernel_model.py, whose phase names A..I this file follows).
 //
 // No floating point, no tensor cores: integer/index work bounded by HBM traffic and shared-memory latency.
+// v2 layout of the per-record state: BITMAPS over record indices (insert / chain-continuation / head / visible) with
+// popcount prefixes per 32-record word, instead of per-record index arrays; everything per-element is derived as
+//   run(i)  = popcount(head bits <= i) - 1
+//   pos(i)  = PosBase[run(i)] + i                 (runs are contiguous in the log AND in the sequence)
+//   vis(i)  = VisBase[run(i)] + popcount(visible bits < i)
 // Working arrays live in a per-CTA ARENA: dynamic shared memory first, a per-CTA global slab (L2 resident) as
 // spill for logs that do not fit.  Index arrays are u16 when the log is small enough (halves the footprint).
 #pragma once
@@ -44,49 +49,54 @@ struct BatchParams {
 // ---------------------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ld_rec(const pt_insdel_rec* p) {
-    return __ldg(reinterpret_cast<const uint4*>(p));
-}
-__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
-__device__ __forceinline__ uint32_t lanemask_le() { uint32_t m; asm("mov.u32 %0, %%lanemask_le;" : "=r"(m)); return m; }
+__device__ __forceinline__ uint4 ld_rec(const pt_insdel_rec* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int BLOCK>
 struct BlockCtx {
-    // static shared scratch shared by all phases
-    uint32_t warp_sums[32];
-    uint32_t scan_total;
+    uint32_t warp_a[32], warp_b[32];
+    uint32_t tot_a, tot_b;
     uint32_t status;
-    uint32_t work;
-    uint32_t n_ins;        // number of insert records (elements)
-    uint32_t M;            // number of runs
-    uint32_t nvis;
-    uint32_t misc[8];
+    uint32_t work, work_next;
+    uint32_t misc[4];
     unsigned long long dig0, dig1;
     unsigned long long pool_base;
 };
 
-// exclusive block scan of one value per thread; returns exclusive prefix, total via ctx (valid after return)
+// exclusive block scan of a PAIR of values per thread (two independent sums in one pass)
 template <int BLOCK>
-__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, BlockCtx<BLOCK>& c, uint32_t& total) {
+__device__ __forceinline__ void block_scan2(uint32_t va, uint32_t vb, BlockCtx<BLOCK>& c, uint32_t& ea, uint32_t& eb,
+                                            uint32_t& ta, uint32_t& tb) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t x = v;
+    uint32_t xa = va, xb = vb;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
-    if (lane == 31) c.warp_sums[warp] = x;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+        if (lane >= (uint32_t)o) { xa += ya; xb += yb; }
+    }
+    if (lane == 31) { c.warp_a[warp] = xa; c.warp_b[warp] = xb; }
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = lane < (BLOCK / 32) ? c.warp_sums[lane] : 0;
-        uint32_t s = w;
+        uint32_t wa = lane < (BLOCK / 32) ? c.warp_a[lane] : 0, wb = lane < (BLOCK / 32) ? c.warp_b[lane] : 0;
+        uint32_t sa = wa, sb = wb;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= (uint32_t)o) s += y; }
-        if (lane < (BLOCK / 32)) c.warp_sums[lane] = s - w;
-        if (lane == 31) c.scan_total = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t ya = __shfl_up_sync(0xffffffffu, sa, o), yb = __shfl_up_sync(0xffffffffu, sb, o);
+            if (lane >= (uint32_t)o) { sa += ya; sb += yb; }
+        }
+        if (lane < (BLOCK / 32)) { c.warp_a[lane] = sa - wa; c.warp_b[lane] = sb - wb; }
+        if (lane == 31) { c.tot_a = sa; c.tot_b = sb; }
     }
     __syncthreads();
-    uint32_t res = c.warp_sums[warp] + x - v;
-    total = c.scan_total;
-    __syncthreads();   // warp_sums reusable
-    return res;
+    ea = c.warp_a[warp] + xa - va; eb = c.warp_b[warp] + xb - vb;
+    ta = c.tot_a; tb = c.tot_b;
+    __syncthreads();
+}
+template <int BLOCK>
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, BlockCtx<BLOCK>& c, uint32_t& total) {
+    uint32_t ea, eb, tb;
+    block_scan2<BLOCK>(v, 0u, c, ea, eb, total, tb);
+    return ea;
 }
 
 struct Arena {
@@ -101,20 +111,40 @@ struct Arena {
     }
 };
 
+// fill `count` elements (allocation is padded to 16 B, so whole uint4 stores are safe)
 template <class T, int BLOCK>
-__device__ __forceinline__ void fill(T* p, uint32_t n, T v) {
-    for (uint32_t i = threadIdx.x; i < n; i += BLOCK) p[i] = v;
+__device__ __forceinline__ void fill(T* p, uint32_t count, T v) {
+    uint32_t nvec = (uint32_t)((count * sizeof(T) + 15u) >> 4);
+    uint32_t w;
+    if (sizeof(T) == 1) w = 0x01010101u * (uint32_t)(uint8_t)v;
+    else if (sizeof(T) == 2) w = 0x00010001u * (uint32_t)(uint16_t)v;
+    else w = (uint32_t)v;
+    uint4 q = make_uint4(w, w, w, w);
+    uint4* d = reinterpret_cast<uint4*>(p);
+    for (uint32_t i = threadIdx.x; i < nvec; i += BLOCK) d[i] = q;
 }
 
-__device__ __forceinline__ void digest_add(unsigned long long& d0, unsigned long long& d1, uint64_t t) {
-    d0 += t; d1 += pt_term_hi(t);
+// 32 byte-flags (0/1) -> one 32-bit word
+__device__ __forceinline__ uint32_t pack32(const uint8_t* b) {
+    const uint4* q = reinterpret_cast<const uint4*>(b);
+    uint4 x = q[0], y = q[1];
+    auto nib = [](uint32_t v) -> uint32_t { return ((v * 0x00204081u) >> 21) & 0xFu; };
+    return nib(x.x) | (nib(x.y) << 4) | (nib(x.z) << 8) | (nib(x.w) << 12) | (nib(y.x) << 16) | (nib(y.y) << 20) | (nib(y.z) << 24) | (nib(y.w) << 28);
 }
 
+__device__ __forceinline__ void digest_add(unsigned long long& d0, unsigned long long& d1, uint64_t t) { d0 += t; d1 += pt_term_hi(t); }
 template <int BLOCK>
 __device__ __forceinline__ void digest_flush(BlockCtx<BLOCK>& c, unsigned long long d0, unsigned long long d1) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&c.dig0, d0); atomicAdd(&c.dig1, d1); }
+    if ((threadIdx.x & 31) == 0 && (d0 | d1)) { atomicAdd(&c.dig0, d0); atomicAdd(&c.dig1, d1); }
+}
+
+// Euler-tour node: next (20 bits) | element weight (22 bits) | visible weight (22 bits)
+constexpr uint32_t kNodeNxtBits = 20;
+constexpr unsigned long long kNodeNxtMask = (1ull << kNodeNxtBits) - 1;
+__device__ __forceinline__ unsigned long long node_make(uint32_t nxt, uint32_t wel, uint32_t wvis) {
+    return (unsigned long long)nxt | ((unsigned long long)wel << 20) | ((unsigned long long)wvis << 42);
 }
 
 // =========================================================================================================
@@ -138,148 +168,178 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
     A.sm = smem_arena; A.sm_cap = P.smem_arena_bytes; A.sm_used = 0;
     A.gm = P.slab + (unsigned long long)blockIdx.x * P.slab_bytes; A.gm_cap = P.slab_bytes; A.gm_used = 0; A.overflow = false;
 
-    if (tid == 0) { c.status = 0; c.n_ins = 0; c.M = 0; c.nvis = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
+    if (tid == 0) { c.status = 0; c.misc[0] = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
 
     auto keyOf = [&](uint32_t ctr, uint32_t actor) -> uint32_t { return (ctr - 1u) * R + actor; };
     auto badId = [&](uint32_t ctr, uint32_t actor) -> bool { return ctr - 1u >= C || actor >= R; };
     auto fail = [&](uint32_t code) { atomicMax(&c.status, code); };
+    auto bail = [&]() { if (tid == 0) { pt_log_result r{}; r.status = c.status; *res = r; } __syncthreads(); };
 
-    // ---- arrays that live through most phases (allocation order = smem priority) ---------------------------
-    Idx* T = A.alloc<Idx>(KS);            // A: opId key -> insert record index
-    Idx* Par = A.alloc<Idx>(n);           // B: parent record index | n (HEAD) | NONE (not an insert)
-    Idx* RunOrPos = A.alloc<Idx>(n);      // C: run id, overwritten by sequence position in F
-    Idx* AnyChild = A.alloc<Idx>(n + 1);  // B: some child of each element (slot n = HEAD)
-    uint8_t* Multi = A.alloc<uint8_t>(n + 1);   // B2: element has >= 2 children
-    uint8_t* Del = A.alloc<uint8_t>(n);         // B: tombstone flag per record index
+    const uint32_t NWr = (n + 31) / 32 + 1;     // words over record indices (+1 zero pad word)
+
+    // ---- arrays that live to the end (allocation order = smem priority) --------------------------------------
+    Idx* T = A.alloc<Idx>(KS);                    // A: opId key -> insert record index
+    uint32_t* InsBits = A.alloc<uint32_t>(NWr);   // record is an insert
+    uint32_t* HeadBits = A.alloc<uint32_t>(NWr);  // record starts a run (first: chain-continuation bits)
+    uint32_t* VisBits = A.alloc<uint32_t>(NWr);   // record is a visible element
+    Idx* HeadPre = A.alloc<Idx>(NWr);             // heads in words < w
+    Idx* VisPre = A.alloc<Idx>(NWr);              // visible elements in words < w
+    // byte flags, dead after phase C (released)
+    const uint32_t mark_sm = A.sm_used; const unsigned long long mark_gm = A.gm_used;
+    uint8_t* Other = A.alloc<uint8_t>(NWr * 32 + 32);   // element has a child that is not its log successor
+    uint8_t* Del = A.alloc<uint8_t>(NWr * 32 + 32);     // tombstone
 
     fill<Idx, BLOCK>(T, KS, NONE);
-    fill<Idx, BLOCK>(AnyChild, n + 1, NONE);
-    fill<uint8_t, BLOCK>(Multi, n + 1, (uint8_t)0);
-    fill<uint8_t, BLOCK>(Del, n, (uint8_t)0);
+    fill<uint8_t, BLOCK>(Other, NWr * 32 + 32, (uint8_t)0);
+    fill<uint8_t, BLOCK>(Del, NWr * 32 + 32, (uint8_t)0);
+    if (tid == 0) { InsBits[NWr - 1] = 0; HeadBits[NWr - 1] = 0; }
     __syncthreads();
 
-    // ---- A: id table ---------------------------------------------------------------------------------------
-    {
-        uint32_t cnt = 0;
-        for (uint32_t i = tid; i < n; i += BLOCK) {
-            uint4 r = ld_rec(ins + i);
-            uint32_t ctr = r.x, actor = r.z & 0xFFFFu, kind = r.w >> 30;
-            if (kind > 1u) { fail(PT_LOG_BAD_KIND); continue; }
-            if (badId(ctr, actor)) { fail(PT_LOG_BAD_OPID); continue; }
-            if (kind == PT_KIND_INSERT) { T[keyOf(ctr, actor)] = (Idx)i; cnt++; }
+    // ---- A: id table + insert / chain-continuation bitmaps (first and only HBM read of the records) ------------
+    // cand(i): record i is an insert whose reference element is the insert at record i-1 (a typing chain link)
+    for (uint32_t base = 0; base < n; base += BLOCK) {
+        const uint32_t i = base + tid;
+        uint32_t ctr = 0, actor = 0, ref_ctr = 0, ref_actor = 0;
+        bool isIns = false;
+        if (i < n) {
+            const uint4 r = ld_rec(ins + i);
+            ctr = r.x; actor = r.z & 0xFFFFu; ref_ctr = r.y; ref_actor = r.z >> 16;
+            const uint32_t kind = r.w >> 30;
+            if (kind > 1u) fail(PT_LOG_BAD_KIND);
+            else if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
+            else if (kind == PT_KIND_INSERT) { isIns = true; T[keyOf(ctr, actor)] = (Idx)i; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0 && cnt) atomicAdd(&c.n_ins, cnt);
+        // id and is-insert flag of record i-1: neighbour lane, one extra load for lane 0
+        uint32_t prev_ctr = __shfl_up_sync(0xffffffffu, ctr, 1);
+        uint32_t prev_pack = __shfl_up_sync(0xffffffffu, actor | (isIns ? 0x10000u : 0u), 1);
+        if (lane == 0) {
+            prev_ctr = 0; prev_pack = 0;
+            if (i > 0 && i < n) { const uint4 r = ld_rec(ins + i - 1); prev_ctr = r.x; prev_pack = (r.z & 0xFFFFu) | (((r.w >> 30) == PT_KIND_INSERT) ? 0x10000u : 0u); }
+        }
+        bool cand = isIns && ref_ctr != 0 && ref_ctr == prev_ctr && (ref_actor | 0x10000u) == prev_pack;
+        if (cand && keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); cand = false; }
+        const uint32_t insW = __ballot_sync(0xffffffffu, isIns), candW = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0 && i < n) { InsBits[i >> 5] = insW; HeadBits[i >> 5] = candW; }
     }
     __syncthreads();
-    if (c.status) { if (tid == 0) { pt_log_result r{}; r.status = c.status; *res = r; } __syncthreads(); return; }
-    const uint32_t N = c.n_ins;
+    if (c.status) { bail(); return; }
 
-    // ---- B: parents, deletes (+ duplicate-id detection) ---------------------------------------------------------
-    for (uint32_t i = tid; i < n; i += BLOCK) {
+    // ---- B: parents of chain heads (-> "has another child" flags), deletes (-> tombstones) ------------------------
+    for (uint32_t base = 0; base < n; base += BLOCK) {
+        const uint32_t i = base + tid;
+        if (i >= n) continue;
+        if ((HeadBits[i >> 5] >> (i & 31)) & 1u) continue;            // chain link: parent is record i-1, no lookup
         uint4 r = ld_rec(ins + i);
-        uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16, kind = r.w >> 30;
+        const uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16, kind = r.w >> 30;
         if (kind == PT_KIND_INSERT) {
-            uint32_t k = keyOf(ctr, actor);
-            if (T[k] != (Idx)i) fail(PT_LOG_BAD_OPID);          // two inserts with one opId
-            uint32_t p;
-            if (ref_ctr == 0) p = n;
-            else {
-                Idx j = badId(ref_ctr, ref_actor) ? NONE : T[keyOf(ref_ctr, ref_actor)];
-                if (j == NONE) { fail(PT_LOG_ELEM_NOT_FOUND); Par[i] = NONE; continue; }
-                if (keyOf(ref_ctr, ref_actor) >= k) { fail(PT_LOG_CYCLE); Par[i] = NONE; continue; }
-                p = j;
-            }
-            Par[i] = (Idx)p;
-            AnyChild[p] = (Idx)i;                                 // arbitrary winner among the children
+            if (ref_ctr == 0) continue;                                 // child of HEAD
+            Idx j = badId(ref_ctr, ref_actor) ? NONE : T[keyOf(ref_ctr, ref_actor)];
+            if (j == NONE) { fail(PT_LOG_ELEM_NOT_FOUND); continue; }
+            if (keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); continue; }
+            Other[j] = 1;
         } else {
-            Par[i] = NONE;
             Idx j = (ref_ctr == 0 || badId(ref_ctr, ref_actor)) ? NONE : T[keyOf(ref_ctr, ref_actor)];
             if (j == NONE) { fail(PT_LOG_ELEM_NOT_FOUND); continue; }
-            Del[j] = 1;                                           // OR over deletes: idempotent (micromerge.ts:689)
+            Del[j] = 1;                                                 // OR over deletes: idempotent (micromerge.ts:689)
         }
     }
     __syncthreads();
-    if (c.status) { if (tid == 0) { pt_log_result r{}; r.status = c.status; *res = r; } __syncthreads(); return; }
-    // B2: flag elements with more than one child (children that lost the AnyChild race reveal it)
-    for (uint32_t i = tid; i < n; i += BLOCK) {
-        Idx p = Par[i];
-        if (p != NONE && AnyChild[p] != (Idx)i) Multi[p] = 1;
-    }
-    __syncthreads();
+    if (c.status) { bail(); return; }
 
-    // ---- C: runs = log-contiguous only-child chains ------------------------------------------------------------------
-    Idx* RunHead = A.alloc<Idx>(N + 1);
-    Idx* RunTail = A.alloc<Idx>(N + 1);
+    // ---- C: runs, bit-parallel: head = insert & (!chain-link | predecessor has another child); visible = insert & !deleted
+    uint32_t M, nvis;
     {
-        uint32_t carry = 0;
-        for (uint32_t base = 0; base < n; base += BLOCK) {
-            uint32_t i = base + tid;
-            bool isIns = false, head = false, tail = false;
-            if (i < n) {
-                Idx p = Par[i];
-                isIns = p != NONE;
-                if (isIns) {
-                    bool cont = i > 0 && (uint32_t)p == i - 1 && !Multi[i - 1];
-                    head = !cont;
-                    bool nextCont = (i + 1 < n) && (uint32_t)Par[i + 1] == i && !Multi[i];
-                    tail = !nextCont;
-                }
+        uint32_t carryH = 0, carryV = 0;
+        for (uint32_t base = 0; base < NWr; base += BLOCK) {
+            const uint32_t w = base + tid;
+            uint32_t head = 0, vis = 0;
+            if (w < NWr) {
+                const uint32_t insW = InsBits[w], candW = HeadBits[w];
+                const uint32_t otherW = pack32(Other + 32 * w), delW = pack32(Del + 32 * w);
+                const uint32_t otherPrev = (otherW << 1) | (w ? (uint32_t)Other[32 * w - 1] : 0u);
+                head = insW & (~candW | otherPrev);
+                vis = insW & ~delW;
             }
-            uint32_t total;
-            uint32_t ex = block_scan_excl<BLOCK>(head ? 1u : 0u, c, total);
-            uint32_t rid = carry + ex + (head ? 1u : 0u) - 1u;     // run id of element i (inclusive count - 1)
-            if (isIns) {
-                RunOrPos[i] = (Idx)rid;
-                if (head) RunHead[rid] = (Idx)i;
-                if (tail) RunTail[rid] = (Idx)i;
-            }
-            carry += total;
+            uint32_t eh, ev, th, tv;
+            block_scan2<BLOCK>(__popc(head), __popc(vis), c, eh, ev, th, tv);
+            if (w < NWr) { HeadBits[w] = head; VisBits[w] = vis; HeadPre[w] = (Idx)(carryH + eh); VisPre[w] = (Idx)(carryV + ev); }
+            carryH += th; carryV += tv;
         }
-        if (tid == 0) c.M = carry;
+        M = carryH; nvis = carryV;
+    }
+    A.sm_used = mark_sm; A.gm_used = mark_gm;      // release Other / Del
+    uint32_t N = 0;
+    {
+        uint32_t cnt = 0;
+        for (uint32_t w = tid; w < NWr; w += BLOCK) cnt += __popc(InsBits[w]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0 && cnt) atomicAdd(&c.misc[0], cnt);
     }
     __syncthreads();
-    const uint32_t M = c.M;
+    N = c.misc[0];
+    if (2ull * M + 4 >= (1ull << kNodeNxtBits) || N >= (1u << 22)) { if (tid == 0) c.status = PT_LOG_OVERFLOW; __syncthreads(); bail(); return; }
+
+    auto runOf = [&](uint32_t i) -> uint32_t {     // run id of element record i
+        return (uint32_t)HeadPre[i >> 5] + __popc(HeadBits[i >> 5] & (0xFFFFFFFFu >> (31 - (i & 31)))) - 1u;
+    };
+    auto visBefore = [&](uint32_t i) -> uint32_t {  // visible element records with index < i   (i in 0..n)
+        return (uint32_t)VisPre[i >> 5] + __popc(VisBits[i >> 5] & ((1u << (i & 31)) - 1u));
+    };
 
     // ---- D: run tree; children of every node ordered by DESCENDING opId of the run head ---------------------------------
+    const uint32_t E = 2 * (M + 1), END = E;
+    unsigned long long* Node = A.alloc<unsigned long long>(E + 1);   // E: Euler-tour nodes (allocated early: hot)
+    Idx* RunHead = A.alloc<Idx>(M + 1);
+    uint32_t* PosBase = A.alloc<uint32_t>(M + 2);   // pos(i) = PosBase[run] + i        (wrap-around arithmetic)
+    uint32_t* VisBase = A.alloc<uint32_t>(M + 2);   // vis(i) = VisBase[run] + visBefore(i)
     Idx* Prun = A.alloc<Idx>(M + 1);
     uint32_t* Key = A.alloc<uint32_t>(M + 1);
-    uint32_t* GrpCnt = A.alloc<uint32_t>(M + 2);    // children per node (node M = HEAD); reused as cursor
+    uint32_t* GrpCnt = VisBase;                     // children per node (node M = HEAD); dead before VisBase is written
+    uint32_t* GrpCur = PosBase;                     // fill cursors; dead before PosBase is written
     Idx* GrpOff = A.alloc<Idx>(M + 2);
     Idx* Unsorted = A.alloc<Idx>(M + 1);
     Idx* Sorted = A.alloc<Idx>(M + 1);
     Idx* SPos = A.alloc<Idx>(M + 1);
     fill<uint32_t, BLOCK>(GrpCnt, M + 2, 0u);
+    fill<uint32_t, BLOCK>(GrpCur, M + 2, 0u);
     __syncthreads();
-    for (uint32_t r = tid; r < M; r += BLOCK) {
-        uint32_t h = RunHead[r];
-        uint32_t p = Par[h];
-        uint32_t q = (p == n) ? M : (uint32_t)RunOrPos[p];
-        Prun[r] = (Idx)q;
-        uint4 rec = ld_rec(ins + h);
-        Key[r] = keyOf(rec.x, rec.z & 0xFFFFu);
-        atomicAdd(&GrpCnt[q], 1u);
+    for (uint32_t w = tid; w < NWr; w += BLOCK) {
+        uint32_t hb = HeadBits[w];
+        uint32_t rid = HeadPre[w];
+        while (hb) {
+            const uint32_t b = __ffs(hb) - 1; hb &= hb - 1;
+            const uint32_t i = w * 32 + b;
+            // run = insert records from i up to the next head or non-insert record
+            uint32_t stop = (HeadBits[w] | ~InsBits[w]) & ~(0xFFFFFFFFu >> (31 - b));
+            uint32_t ww = w;
+            while (!stop) { ww++; stop = HeadBits[ww] | ~InsBits[ww]; }     // pad word: InsBits == 0 -> stops
+            const uint32_t end = ww * 32 + (__ffs(stop) - 1);
+            const uint4 rec = ld_rec(ins + i);
+            const uint32_t p = rec.y == 0 ? n : (uint32_t)T[keyOf(rec.y, rec.z >> 16)];
+            const uint32_t q = p == n ? M : runOf(p);
+            RunHead[rid] = (Idx)i;
+            Node[rid] = node_make(0, end - i, visBefore(end) - visBefore(i));   // weights now, successor in phase E
+            Prun[rid] = (Idx)q;
+            Key[rid] = keyOf(rec.x, rec.z & 0xFFFFu);
+            atomicAdd(&GrpCnt[q], 1u);
+            rid++;
+        }
     }
     __syncthreads();
     {
         uint32_t carry = 0;
         for (uint32_t base = 0; base < M + 1; base += BLOCK) {
-            uint32_t q = base + tid;
-            uint32_t v = q < M + 1 ? GrpCnt[q] : 0u, total;
-            uint32_t ex = block_scan_excl<BLOCK>(v, c, total);
+            uint32_t q = base + tid, total;
+            uint32_t ex = block_scan_excl<BLOCK>(q < M + 1 ? GrpCnt[q] : 0u, c, total);
             if (q < M + 1) GrpOff[q] = (Idx)(carry + ex);
             carry += total;
         }
     }
     __syncthreads();
-    uint32_t* GrpCur = A.alloc<uint32_t>(M + 2);
-    fill<uint32_t, BLOCK>(GrpCur, M + 2, 0u);
-    __syncthreads();
     for (uint32_t r = tid; r < M; r += BLOCK) {
         uint32_t q = Prun[r];
-        uint32_t slot = (uint32_t)GrpOff[q] + atomicAdd(&GrpCur[q], 1u);
-        Unsorted[slot] = (Idx)r;
+        Unsorted[(uint32_t)GrpOff[q] + atomicAdd(&GrpCur[q], 1u)] = (Idx)r;
     }
     __syncthreads();
     for (uint32_t r = tid; r < M; r += BLOCK) {
@@ -292,81 +352,61 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
     __syncthreads();
 
     // ---- E: Euler tour (enter r = r, exit r = (M+1)+r, r in 0..M) + weighted pointer-jumping list ranking ------------------
-    const uint32_t E = 2 * (M + 1), END = E;
-    Idx* nxtA = A.alloc<Idx>(E + 1);
-    Idx* nxtB = A.alloc<Idx>(E + 1);
-    Idx* dA = A.alloc<Idx>(E + 1);
-    Idx* dB = A.alloc<Idx>(E + 1);
+    // One 64-bit word per node: next | element weight | visible weight; invariant: the weights of x cover the nodes from
+    // x up to (excluding) next(x).  A node is read and written as ONE aligned 64-bit word, so jumping in place is safe:
+    // whichever version of the successor a thread reads is self-consistent, and the invariant is preserved.
     for (uint32_t r = tid; r <= M; r += BLOCK) {
-        uint32_t ent = r, ext = (M + 1) + r;
-        uint32_t cnt = GrpCnt[r];
-        nxtA[ent] = (Idx)(cnt ? (uint32_t)Sorted[GrpOff[r]] : ext);
-        dA[ent] = (Idx)(r < M ? (uint32_t)RunTail[r] - (uint32_t)RunHead[r] + 1u : 0u);
-        dA[ext] = 0;
-        if (r == M) nxtA[ext] = (Idx)END;
+        const uint32_t ent = r, ext = (M + 1) + r;
+        const uint32_t cnt = GrpCnt[r];
+        const uint32_t first = cnt ? (uint32_t)Sorted[GrpOff[r]] : ext;
+        Node[ent] = (r < M ? (Node[ent] & ~kNodeNxtMask) : 0ull) | first;
+        uint32_t nx;
+        if (r == M) nx = END;
         else {
-            uint32_t q = Prun[r], sp = SPos[r];
-            bool last = sp + 1 == (uint32_t)GrpOff[q] + GrpCnt[q];
-            nxtA[ext] = (Idx)(last ? (M + 1) + q : (uint32_t)Sorted[sp + 1]);
+            const uint32_t q = Prun[r], sp = SPos[r];
+            const bool last = sp + 1 == (uint32_t)GrpOff[q] + GrpCnt[q];
+            nx = last ? (M + 1) + q : (uint32_t)Sorted[sp + 1];
         }
+        Node[ext] = node_make(nx, 0, 0);
     }
-    if (tid == 0) { nxtA[END] = (Idx)END; dA[END] = 0; nxtB[END] = (Idx)END; dB[END] = 0; }
+    if (tid == 0) Node[END] = node_make(END, 0, 0);
     __syncthreads();
     {
-        Idx *nc = nxtA, *nn = nxtB, *dc = dA, *dn = dB;
+        volatile unsigned long long* vn = Node;
         for (uint32_t span = 1; span < E + 1; span <<= 1) {
             for (uint32_t x = tid; x < E; x += BLOCK) {
-                uint32_t nx = nc[x];
-                dn[x] = (Idx)((uint32_t)dc[x] + (uint32_t)dc[nx]);     // dc[END] == 0
-                nn[x] = nc[nx];                                          // nc[END] == END
+                const unsigned long long a = vn[x];
+                const uint32_t nx = (uint32_t)(a & kNodeNxtMask);
+                if (nx == END) continue;
+                const unsigned long long b = vn[nx];
+                vn[x] = ((a & ~kNodeNxtMask) + (b & ~kNodeNxtMask)) | (b & kNodeNxtMask);
             }
             __syncthreads();
-            Idx* t = nc; nc = nn; nn = t; t = dc; dc = dn; dn = t;
         }
-        dA = dc;   // dA[r] = number of elements from run r to the end of the sequence
     }
+    unsigned long long* nodeA = Node;   // weights of Node[r] = elements / visible elements from run r to the end of the sequence
+    for (uint32_t r = tid; r < M; r += BLOCK) {
+        const unsigned long long a = nodeA[r];
+        const uint32_t sufEl = (uint32_t)(a >> 20) & 0x3FFFFFu, sufVis = (uint32_t)(a >> 42);
+        const uint32_t h = RunHead[r];
+        PosBase[r] = (N - sufEl) - h;
+        VisBase[r] = (nvis - sufVis) - visBefore(h);
+    }
+    __syncthreads();
+    auto posOf = [&](uint32_t i) -> uint32_t { return PosBase[runOf(i)] + i; };                    // sequence position of element record i
+    auto visOf = [&](uint32_t i) -> uint32_t { return VisBase[runOf(i)] + visBefore(i); };         // visible elements before it in the sequence
+    auto isVis = [&](uint32_t i) -> bool { return (VisBits[i >> 5] >> (i & 31)) & 1u; };
 
-    // ---- F: sequence positions, tombstones in sequence order, visible ranks, text ------------------------------------------
-    uint8_t* SeqDel = A.alloc<uint8_t>(N + 1);
-    const uint32_t NW = (N + 32) / 32;              // bit words covering positions 0..N
-    uint32_t* VisBits = A.alloc<uint32_t>(NW + 1);
-    Idx* VisPre = A.alloc<Idx>(NW + 1);
-    for (uint32_t i = tid; i < n; i += BLOCK) {
-        if (Par[i] == NONE) continue;
-        uint32_t r = RunOrPos[i];
-        uint32_t pos = N - (uint32_t)dA[r] + (i - (uint32_t)RunHead[r]);
-        RunOrPos[i] = (Idx)pos;
-        SeqDel[pos] = Del[i];
-    }
-    __syncthreads();
-    {
-        uint32_t carry = 0;
-        for (uint32_t base = 0; base < NW; base += BLOCK) {
-            // each thread builds one 32-position word serially from the byte flags of its 32 positions
-            uint32_t w = base + tid, bits = 0;
-            if (w < NW) {
-                uint32_t x0 = w * 32;
-                for (uint32_t b = 0; b < 32; b++) { uint32_t x = x0 + b; if (x < N && !SeqDel[x]) bits |= 1u << b; }
-                VisBits[w] = bits;
-            }
-            uint32_t total, ex = block_scan_excl<BLOCK>(__popc(bits), c, total);
-            if (w < NW) VisPre[w] = (Idx)(carry + ex);
-            carry += total;
-        }
-        if (tid == 0) c.nvis = carry;
-    }
-    __syncthreads();
-    const uint32_t nvis = c.nvis;
-    auto visRank = [&](uint32_t x) -> uint32_t {   // number of visible elements at positions < x   (x in 0..N)
-        uint32_t w = x >> 5, b = x & 31;
-        return (uint32_t)VisPre[w] + __popc(VisBits[w] & ((1u << b) - 1u));
-    };
+    // ---- F: text out (visible index = prefix count of non-deleted elements, micromerge.ts:747-750) + duplicate-id check --
     {
         unsigned long long d0 = 0, d1 = 0;
         for (uint32_t i = tid; i < n; i += BLOCK) {
-            if (Par[i] == NONE || Del[i]) continue;
-            uint32_t tok = PT_PAYLOAD_TOKEN(__ldg(&ins[i].payload));
-            uint32_t vr = visRank(RunOrPos[i]);
+            if (!((InsBits[i >> 5] >> (i & 31)) & 1u)) continue;
+            const uint4 r = ld_rec(ins + i);
+            if ((uint32_t)T[keyOf(r.x, r.z & 0xFFFFu)] != i) fail(PT_LOG_BAD_OPID);     // two inserts with one opId
+            if (!isVis(i)) continue;
+            const uint32_t tok = PT_PAYLOAD_TOKEN(r.w);
+            const uint32_t vr = visOf(i);
             text_out[vr] = tok;
             digest_add(d0, d1, pt_term_text(vr, tok));
         }
@@ -387,6 +427,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
     } else {
         // ---- G: marks ---------------------------------------------------------------------------------------------------
         // G1: rank mark ops by opId: bitmap over the key space + prefix popcount (a counting sort with unique keys)
+        const uint32_t NWp = (N + 32) / 32 + 1;          // words over sequence positions 0..N
         const uint32_t KW = (KS + 31) / 32;
         uint32_t* KBits = A.alloc<uint32_t>(KW + 1);
         Idx* KPre = A.alloc<Idx>(KW + 1);
@@ -394,11 +435,12 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         Idx* MRank = A.alloc<Idx>(m + 1);
         Idx* IvA = A.alloc<Idx>(m + 1);         // element interval [a,b) per mark op; a == b: covers nothing
         Idx* IvB = A.alloc<Idx>(m + 1);
-        uint8_t* Bnd = A.alloc<uint8_t>(N + 2);   // boundary flags over element indices 0..N
-        uint32_t* BndBits = A.alloc<uint32_t>(NW + 1);
-        Idx* SegPre = A.alloc<Idx>(NW + 1);
+        Idx* IvVA = A.alloc<Idx>(m + 1);        // visible rank of positions a and b
+        Idx* IvVB = A.alloc<Idx>(m + 1);
+        uint32_t* BndBits = A.alloc<uint32_t>(NWp + 1);
+        Idx* SegPre = A.alloc<Idx>(NWp + 1);
         fill<uint32_t, BLOCK>(KBits, KW + 1, 0u);
-        fill<uint8_t, BLOCK>(Bnd, N + 2, (uint8_t)0);
+        fill<uint32_t, BLOCK>(BndBits, NWp + 1, 0u);
         __syncthreads();
         for (uint32_t k = tid; k < m; k += BLOCK) {
             uint32_t ctr = mk[k].ctr, actor = mk[k].actor;
@@ -409,7 +451,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             if (T[key] != NONE) fail(PT_LOG_BAD_OPID);
         }
         __syncthreads();
-        if (c.status) { if (tid == 0) { pt_log_result r{}; r.status = c.status; *res = r; } __syncthreads(); return; }
+        if (c.status) { bail(); return; }
         {
             uint32_t carry = 0;
             for (uint32_t base = 0; base < KW; base += BLOCK) {
@@ -429,37 +471,32 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             uint32_t sb = r.bounds & 3u, eb = (r.bounds >> 2) & 3u;
             // a slot is 2*pos + (after ? 1 : 0); NOSLOT: the walk never matches this boundary (peritext.ts:236-241)
             const uint32_t NOSLOT = 0xFFFFFFFFu;
-            uint32_t ps = NOSLOT, pe = NOSLOT;
+            uint32_t ps = NOSLOT, pe = NOSLOT, vs = 0, ve = nvis;
             if (sb <= PT_BOUND_AFTER && !badId(r.start_ctr, r.start_actor)) {
                 Idx j = T[keyOf(r.start_ctr, r.start_actor)];
-                if (j != NONE) ps = 2u * (uint32_t)RunOrPos[j] + sb;
+                if (j != NONE) { ps = 2u * posOf(j) + sb; vs = visOf(j) + ((sb && isVis(j)) ? 1u : 0u); }
             }
             if (eb <= PT_BOUND_AFTER && !badId(r.end_ctr, r.end_actor)) {
                 Idx j = T[keyOf(r.end_ctr, r.end_actor)];
-                if (j != NONE) pe = 2u * (uint32_t)RunOrPos[j] + eb;
+                if (j != NONE) { pe = 2u * posOf(j) + eb; ve = visOf(j) + ((eb && isVis(j)) ? 1u : 0u); }
             }
             uint32_t a = 0, b = 0;
             if (ps != NOSLOT) {
-                if (pe == ps || pe == NOSLOT) pe = 2u * N;        // same slot: start branch wins, never ends (quirk Q2)
+                if (pe == ps || pe == NOSLOT) { pe = 2u * N; ve = nvis; }   // same slot: start branch wins, never ends (quirk Q2)
                 a = (ps + 1u) >> 1; b = (pe + 1u) >> 1; if (b > N) b = N;
                 if (a >= b) { a = 0; b = 0; }
             }
-            IvA[k] = (Idx)a; IvB[k] = (Idx)b;
-            if (a < b) { Bnd[a] = 1; Bnd[b] = 1; }
+            IvA[k] = (Idx)a; IvB[k] = (Idx)b; IvVA[k] = (Idx)vs; IvVB[k] = (Idx)ve;
+            if (a < b) { atomicOr(&BndBits[a >> 5], 1u << (a & 31)); atomicOr(&BndBits[b >> 5], 1u << (b & 31)); }
         }
         __syncthreads();
         uint32_t S;   // number of segment ids: seg(x) in [0, S)
         {
             uint32_t carry = 0;
-            for (uint32_t base = 0; base < NW; base += BLOCK) {
-                uint32_t w = base + tid, bits = 0;
-                if (w < NW) {
-                    uint32_t x0 = w * 32;
-                    for (uint32_t b = 0; b < 32; b++) { uint32_t x = x0 + b; if (x <= N && Bnd[x]) bits |= 1u << b; }
-                    BndBits[w] = bits;
-                }
-                uint32_t total, ex = block_scan_excl<BLOCK>(__popc(bits), c, total);
-                if (w < NW) SegPre[w] = (Idx)(carry + ex);
+            for (uint32_t base = 0; base < NWp; base += BLOCK) {
+                uint32_t w = base + tid, total;
+                uint32_t ex = block_scan_excl<BLOCK>(w < NWp ? __popc(BndBits[w]) : 0u, c, total);
+                if (w < NWp) SegPre[w] = (Idx)(carry + ex);
                 carry += total;
             }
             S = carry + 1;
@@ -506,16 +543,16 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         }
         // G4: `comment` key present iff at least one comment op (add or remove) covers the segment (quirk Q3)
         uint32_t* CompactC = A.alloc<uint32_t>(m + 1);     // indices of non-empty comment ops
-        if (tid == 0) c.misc[0] = 0;
+        if (tid == 0) c.misc[1] = 0;
         __syncthreads();
         for (uint32_t k = tid; k < m; k += BLOCK) {
             uint32_t a = IvA[k], b = IvB[k];
             if (a >= b || ((uint32_t)(mk[k].kind >> 1) & 3u) != PT_MARK_COMMENT) continue;
             atomicAdd(&CDiff[segOf(a)], 1); atomicAdd(&CDiff[segOf(b)], -1);
-            CompactC[atomicAdd(&c.misc[0], 1u)] = k;
+            CompactC[atomicAdd(&c.misc[1], 1u)] = k;
         }
         __syncthreads();
-        const uint32_t Mc = c.misc[0];
+        const uint32_t Mc = c.misc[1];
         {
             int carry = 0;
             for (uint32_t base = 0; base < S; base += BLOCK) {
@@ -541,15 +578,16 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             uint32_t ci = e >> 1, which = e & 1u, k = CompactC[ci];
             uint32_t id = mk[k].attr;
             uint32_t x = which ? (uint32_t)IvB[k] : (uint32_t)IvA[k];
-            bool dup = false; uint32_t nextEnd = 0xFFFFFFFFu;
+            uint32_t xv = which ? (uint32_t)IvVB[k] : (uint32_t)IvVA[k];
+            bool dup = false; uint32_t nextEnd = 0xFFFFFFFFu, nextV = 0;
             for (uint32_t cj = 0; cj < Mc; cj++) {
                 uint32_t j = CompactC[cj];
                 if (mk[j].attr != id) continue;
                 uint32_t ja = IvA[j], jb = IvB[j];
                 if (ja == x && (cj < ci || (cj == ci && 0u < which))) dup = true;
                 if (jb == x && (cj < ci || (cj == ci && 1u < which))) dup = true;
-                if (ja > x && ja < nextEnd) nextEnd = ja;
-                if (jb > x && jb < nextEnd) nextEnd = jb;
+                if (ja > x && ja < nextEnd) { nextEnd = ja; nextV = IvVA[j]; }
+                if (jb > x && jb < nextEnd) { nextEnd = jb; nextV = IvVB[j]; }
             }
             uint32_t va = 0, vb = 0;
             if (!dup && nextEnd != 0xFFFFFFFFu) {
@@ -562,7 +600,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
                         if (rk > best) { best = rk; bestAdd = (mk[j].kind & 1u) == 0; }
                     }
                 }
-                if (best && bestAdd) { va = visRank(x); vb = visRank(nextEnd); if (va >= vb) { va = 0; vb = 0; } }
+                if (best && bestAdd) { va = xv; vb = nextV; if (va >= vb) { va = 0; vb = 0; } }
             }
             PcId[e] = id; PcA[e] = (Idx)va; PcB[e] = (Idx)vb;
         }
@@ -585,12 +623,11 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         // ---- I: spans ---------------------------------------------------------------------------------------------------
         Idx* VisSeg = A.alloc<Idx>(nvis + 1);
         const uint32_t VW = (nvis + 31) / 32;
-        uint32_t* HeadBits = A.alloc<uint32_t>(VW + 1);
-        Idx* HeadPre = A.alloc<Idx>(VW + 1);
+        uint32_t* HeadB = A.alloc<uint32_t>(VW + 1);
+        Idx* HeadP = A.alloc<Idx>(VW + 1);
         for (uint32_t i = tid; i < n; i += BLOCK) {
-            if (Par[i] == NONE || Del[i]) continue;
-            uint32_t pos = RunOrPos[i];
-            VisSeg[visRank(pos)] = (Idx)(segOf(pos) );
+            if (!isVis(i)) continue;
+            VisSeg[visOf(i)] = (Idx)segOf(posOf(i));
         }
         __syncthreads();
         {
@@ -610,10 +647,10 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
                         }
                         if (h) bits |= 1u << b;
                     }
-                    HeadBits[w] = bits;
+                    HeadB[w] = bits;
                 }
                 uint32_t total, ex = block_scan_excl<BLOCK>(__popc(bits), c, total);
-                if (w < VW) HeadPre[w] = (Idx)(carry + ex);
+                if (w < VW) HeadP[w] = (Idx)(carry + ex);
                 carry += total;
             }
             nspans = carry;
@@ -622,7 +659,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         auto headRank = [&](uint32_t v) -> uint32_t {   // number of span heads at visible positions < v  (v in 0..nvis)
             uint32_t w = v >> 5, b = v & 31;
             if (w >= VW) return nspans;
-            return (uint32_t)HeadPre[w] + __popc(HeadBits[w] & ((1u << b) - 1u));
+            return (uint32_t)HeadP[w] + __popc(HeadB[w] & ((1u << b) - 1u));
         };
         // comment lists per span: count, reserve pool space, fill, sort
         uint32_t* SpanCC = A.alloc<uint32_t>(nspans + 1);
@@ -657,7 +694,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             c.pool_base = base;
         }
         __syncthreads();
-        if (c.status) { if (tid == 0) { pt_log_result r{}; r.status = c.status; *res = r; } __syncthreads(); return; }
+        if (c.status) { bail(); return; }
         uint32_t* pool = P.comment_pool + c.pool_base;
         for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
             uint32_t va = PcA[e], vb = PcB[e];
@@ -669,7 +706,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         {
             unsigned long long d0 = 0, d1 = 0;
             for (uint32_t w = tid; w < VW; w += BLOCK) {
-                uint32_t bits = HeadBits[w], j = HeadPre[w];
+                uint32_t bits = HeadB[w], j = HeadP[w];
                 while (bits) {
                     uint32_t b = __ffs(bits) - 1; bits &= bits - 1;
                     uint32_t v = w * 32 + b, s = VisSeg[v];
@@ -704,17 +741,27 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
     __syncthreads();
 }
 
-// Persistent CTAs pull logs from the bin's work queue.
+// Persistent CTAs pull logs from the bin's work queue; the next log's records are prefetched into L2 while the
+// current one is processed.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) merge_logs_kernel(const BatchParams P) {
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : BLOCK == 128 ? 7 : 1)) merge_logs_kernel(const BatchParams P) {
     extern __shared__ __align__(16) char smem_arena[];
     __shared__ BlockCtx<BLOCK> ctx;
+    if (threadIdx.x == 0) ctx.work_next = atomicAdd(P.work_counter, 1u);
+    __syncthreads();
     for (;;) {
-        if (threadIdx.x == 0) ctx.work = atomicAdd(P.work_counter, 1u);
-        __syncthreads();
-        const uint32_t w = ctx.work;
+        const uint32_t w = ctx.work_next;
         __syncthreads();
         if (w >= P.n_work) break;
+        if (threadIdx.x == 0) ctx.work_next = atomicAdd(P.work_counter, 1u);
+        __syncthreads();
+        const uint32_t wn = ctx.work_next;
+        if (wn < P.n_work) {
+            const pt_log_desc& Ln = P.desc[P.order[wn]];
+            const char* p0 = reinterpret_cast<const char*>(P.insdel + Ln.insdel_off);
+            const uint32_t lines = (uint32_t)(((unsigned long long)Ln.n_insdel * sizeof(pt_insdel_rec) + 127) >> 7);
+            for (uint32_t l = threadIdx.x; l < lines; l += BLOCK) prefetch_l2(p0 + ((size_t)l << 7));
+        }
         const uint32_t li = P.order[w];
         const pt_log_desc& L = P.desc[li];
         const bool small = L.n_insdel < 32000u && L.n_mark < 32000u;
