@@ -79,11 +79,13 @@ size_t arena_worst_bytes(uint64_t n, uint64_t m, uint64_t KS) {
     if (m) {
         const uint64_t KW = KS / 32 + 2, S = 2 * m + 2, Mc = m, nsp = 2 * m + 1, NWp = (n + 32) / 32 + 1;
         A(KW + 1, 4); A(KW + 1, I); for (int k = 0; k < 6; k++) A(m + 1, I);       // KBits KPre ByRank MRank IvA IvB IvVA IvVB
+        A(m + 1, 1); A(m + 1, 4); A(m + 1, 4);                                     // MKind MAttr CompactC
         A(NWp + 1, 4); A(NWp + 1, I);                                              // BndBits SegPre
-        A(2 * S + 2, 4); A(S + 1, 4); A(S + 1, 4); A(S + 2, 4); A(m + 1, 4);       // Tree SegFlags SegLink CDiff CompactC
-        A(n / 32 + 3, 4); A(2 * Mc + 1, 4); A(2 * Mc + 1, I); A(2 * Mc + 1, I);    // CHead PcId PcA PcB
+        A(3 * (2 * S + 2), 4); A(S + 1, 4); A(S + 1, 4); A(S + 2, 4);              // Tree[3] SegFlags SegLink CDiff
+        A(n / 32 + 3, 4); A(Mc + 1, 4); A(Mc + 1, I); A(Mc + 1, I); A(Mc + 1, I);  // CHead CId CK CG0 CGn
+        A(2 * Mc + 1, I); A(2 * Mc + 1, I);                                        // PcA PcB
         A(n + 1, I); A(n / 32 + 2, 4); A(n / 32 + 2, I);                           // VisSeg HeadB HeadP
-        A(nsp + 1, 4); A(nsp + 1, 4); A(nsp + 1, 4);                               // SpanCC SpanCO SpanCur
+        A(nsp + 1, I); A(nsp + 1, 4); A(nsp + 1, 4); A(nsp + 1, 4);                // SpanStart SpanCC SpanCO SpanCur
     }
     return b + 256;
 }

@@ -437,10 +437,13 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         Idx* IvB = A.alloc<Idx>(m + 1);
         Idx* IvVA = A.alloc<Idx>(m + 1);        // visible rank of positions a and b
         Idx* IvVB = A.alloc<Idx>(m + 1);
+        uint8_t* MKind = A.alloc<uint8_t>(m + 1);   // pt_mark_rec.kind (bit0 remove, bits2:1 type)
+        uint32_t* MAttr = A.alloc<uint32_t>(m + 1);
         uint32_t* BndBits = A.alloc<uint32_t>(NWp + 1);
         Idx* SegPre = A.alloc<Idx>(NWp + 1);
         fill<uint32_t, BLOCK>(KBits, KW + 1, 0u);
         fill<uint32_t, BLOCK>(BndBits, NWp + 1, 0u);
+        if (tid == 0) { c.misc[1] = 0; }
         __syncthreads();
         for (uint32_t k = tid; k < m; k += BLOCK) {
             uint32_t ctr = mk[k].ctr, actor = mk[k].actor;
@@ -462,22 +465,27 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             }
         }
         __syncthreads();
-        // G2: boundary slots -> element intervals
+        // G2: boundary slots -> element intervals; comment ops are compacted on the side
+        uint32_t* CompactC = A.alloc<uint32_t>(m + 1);     // indices of non-empty comment ops
         for (uint32_t k = tid; k < m; k += BLOCK) {
-            const pt_mark_rec r = mk[k];
-            uint32_t key = keyOf(r.ctr, r.actor);
+            const uint4* q = reinterpret_cast<const uint4*>(mk + k);
+            const uint4 r0 = __ldg(q), r1 = __ldg(q + 1);
+            // r0 = {ctr, actor|kind<<16|bounds<<24, start_ctr, end_ctr}; r1 = {start_actor|end_actor<<16, attr, arrival, reserved}
+            const uint32_t ctr = r0.x, actor = r0.y & 0xFFFFu, kind = (r0.y >> 16) & 0xFFu, bounds = r0.y >> 24;
+            const uint32_t start_ctr = r0.z, end_ctr = r0.w, start_actor = r1.x & 0xFFFFu, end_actor = r1.x >> 16, attr = r1.y;
+            uint32_t key = keyOf(ctr, actor);
             uint32_t rank = (uint32_t)KPre[key >> 5] + __popc(KBits[key >> 5] & ((1u << (key & 31)) - 1u));
-            MRank[k] = (Idx)rank; ByRank[rank] = (Idx)k;
-            uint32_t sb = r.bounds & 3u, eb = (r.bounds >> 2) & 3u;
+            MRank[k] = (Idx)rank; ByRank[rank] = (Idx)k; MKind[k] = (uint8_t)kind; MAttr[k] = attr;
+            uint32_t sb = bounds & 3u, eb = (bounds >> 2) & 3u;
             // a slot is 2*pos + (after ? 1 : 0); NOSLOT: the walk never matches this boundary (peritext.ts:236-241)
             const uint32_t NOSLOT = 0xFFFFFFFFu;
             uint32_t ps = NOSLOT, pe = NOSLOT, vs = 0, ve = nvis;
-            if (sb <= PT_BOUND_AFTER && !badId(r.start_ctr, r.start_actor)) {
-                Idx j = T[keyOf(r.start_ctr, r.start_actor)];
+            if (sb <= PT_BOUND_AFTER && !badId(start_ctr, start_actor)) {
+                Idx j = T[keyOf(start_ctr, start_actor)];
                 if (j != NONE) { ps = 2u * posOf(j) + sb; vs = visOf(j) + ((sb && isVis(j)) ? 1u : 0u); }
             }
-            if (eb <= PT_BOUND_AFTER && !badId(r.end_ctr, r.end_actor)) {
-                Idx j = T[keyOf(r.end_ctr, r.end_actor)];
+            if (eb <= PT_BOUND_AFTER && !badId(end_ctr, end_actor)) {
+                Idx j = T[keyOf(end_ctr, end_actor)];
                 if (j != NONE) { pe = 2u * posOf(j) + eb; ve = visOf(j) + ((eb && isVis(j)) ? 1u : 0u); }
             }
             uint32_t a = 0, b = 0;
@@ -487,9 +495,13 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
                 if (a >= b) { a = 0; b = 0; }
             }
             IvA[k] = (Idx)a; IvB[k] = (Idx)b; IvVA[k] = (Idx)vs; IvVB[k] = (Idx)ve;
-            if (a < b) { atomicOr(&BndBits[a >> 5], 1u << (a & 31)); atomicOr(&BndBits[b >> 5], 1u << (b & 31)); }
+            if (a < b) {
+                atomicOr(&BndBits[a >> 5], 1u << (a & 31)); atomicOr(&BndBits[b >> 5], 1u << (b & 31));
+                if (((kind >> 1) & 3u) == PT_MARK_COMMENT) CompactC[atomicAdd(&c.misc[1], 1u)] = k;
+            }
         }
         __syncthreads();
+        const uint32_t Mc = c.misc[1];
         uint32_t S;   // number of segment ids: seg(x) in [0, S)
         {
             uint32_t carry = 0;
@@ -506,84 +518,86 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             uint32_t w = x >> 5, b = x & 31;
             return (uint32_t)SegPre[w] + __popc(BndBits[w] & (0xFFFFFFFFu >> (31 - b)));
         };
-        // G3: stabbing max per LWW type on an iterative segment tree over segment ids (range atomicMax, point query)
-        uint32_t* Tree = A.alloc<uint32_t>(2 * S + 2);
+        // G3: stabbing max per LWW type: three iterative segment trees over segment ids (range atomicMax, point query)
+        const uint32_t TS = 2 * S + 2;
+        uint32_t* Tree = A.alloc<uint32_t>(3 * TS);      // [strong | em | link]
         uint32_t* SegFlags = A.alloc<uint32_t>(S + 1);
         uint32_t* SegLink = A.alloc<uint32_t>(S + 1);
         int* CDiff = A.alloc<int>(S + 2);
-        for (uint32_t s = tid; s < S + 1; s += BLOCK) { SegFlags[s] = 0; SegLink[s] = PT_ATTR_NONE; }
+        fill<uint32_t, BLOCK>(Tree, 3 * TS, 0u);
         fill<int, BLOCK>(CDiff, S + 2, 0);
-        for (uint32_t t = 0; t < 4; t++) {
-            if (t == PT_MARK_COMMENT) continue;
-            fill<uint32_t, BLOCK>(Tree, 2 * S + 2, 0u);
-            __syncthreads();
-            for (uint32_t k = tid; k < m; k += BLOCK) {
-                uint32_t a = IvA[k], b = IvB[k];
-                if (a >= b || ((uint32_t)(mk[k].kind >> 1) & 3u) != t) continue;
-                uint32_t v = (uint32_t)MRank[k] + 1u;
-                for (uint32_t l = segOf(a) + S, r = segOf(b) + S; l < r; l >>= 1, r >>= 1) {
-                    if (l & 1u) atomicMax(&Tree[l++], v);
-                    if (r & 1u) atomicMax(&Tree[--r], v);
-                }
-            }
-            __syncthreads();
-            const uint32_t bit = t == PT_MARK_STRONG ? PT_SPAN_STRONG : t == PT_MARK_EM ? PT_SPAN_EM : PT_SPAN_LINK;
-            for (uint32_t s = tid; s < S; s += BLOCK) {
-                uint32_t w = 0;
-                for (uint32_t p = s + S; p >= 1; p >>= 1) w = max(w, Tree[p]);
-                if (w) {
-                    uint32_t kk = ByRank[w - 1];
-                    if ((mk[kk].kind & 1u) == 0) {                         // winner is an addMark (peritext.ts:307-311)
-                        SegFlags[s] |= bit;
-                        if (t == PT_MARK_LINK) SegLink[s] = mk[kk].attr;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        // G4: `comment` key present iff at least one comment op (add or remove) covers the segment (quirk Q3)
-        uint32_t* CompactC = A.alloc<uint32_t>(m + 1);     // indices of non-empty comment ops
-        if (tid == 0) c.misc[1] = 0;
         __syncthreads();
         for (uint32_t k = tid; k < m; k += BLOCK) {
-            uint32_t a = IvA[k], b = IvB[k];
-            if (a >= b || ((uint32_t)(mk[k].kind >> 1) & 3u) != PT_MARK_COMMENT) continue;
-            atomicAdd(&CDiff[segOf(a)], 1); atomicAdd(&CDiff[segOf(b)], -1);
-            CompactC[atomicAdd(&c.misc[1], 1u)] = k;
+            const uint32_t a = IvA[k], b = IvB[k];
+            if (a >= b) continue;
+            const uint32_t t = ((uint32_t)MKind[k] >> 1) & 3u;
+            const uint32_t sa = segOf(a), sb2 = segOf(b);
+            if (t == PT_MARK_COMMENT) { atomicAdd(&CDiff[sa], 1); atomicAdd(&CDiff[sb2], -1); continue; }   // G4 difference array
+            uint32_t* tr = Tree + (t == PT_MARK_STRONG ? 0u : t == PT_MARK_EM ? TS : 2 * TS);
+            const uint32_t v = (uint32_t)MRank[k] + 1u;
+            for (uint32_t l = sa + S, r = sb2 + S; l < r; l >>= 1, r >>= 1) {
+                if (l & 1u) atomicMax(&tr[l++], v);
+                if (r & 1u) atomicMax(&tr[--r], v);
+            }
         }
         __syncthreads();
-        const uint32_t Mc = c.misc[1];
+        // per segment: LWW winners (peritext.ts:304-313) and G4 `comment` key present iff >= 1 comment op covers it (quirk Q3)
         {
             int carry = 0;
             for (uint32_t base = 0; base < S; base += BLOCK) {
-                uint32_t s = base + tid, total;
-                int v = s < S ? CDiff[s] : 0;
-                uint32_t ex = block_scan_excl<BLOCK>((uint32_t)v, c, total);   // two's complement sums are fine
-                int cover = carry + (int)ex + v;
-                if (s < S && cover > 0) SegFlags[s] |= PT_SPAN_COMMENT;
+                const uint32_t s2 = base + tid;
+                uint32_t flags = 0, link = PT_ATTR_NONE;
+                int v = 0;
+                if (s2 < S) {
+                    uint32_t w0 = 0, w1 = 0, w2 = 0;
+                    for (uint32_t p = s2 + S; p >= 1; p >>= 1) { w0 = max(w0, Tree[p]); w1 = max(w1, Tree[TS + p]); w2 = max(w2, Tree[2 * TS + p]); }
+                    if (w0 && !(MKind[ByRank[w0 - 1]] & 1u)) flags |= PT_SPAN_STRONG;
+                    if (w1 && !(MKind[ByRank[w1 - 1]] & 1u)) flags |= PT_SPAN_EM;
+                    if (w2) { const uint32_t kk = ByRank[w2 - 1]; if (!(MKind[kk] & 1u)) { flags |= PT_SPAN_LINK; link = MAttr[kk]; } }
+                    v = CDiff[s2];
+                }
+                uint32_t total;
+                const uint32_t ex = block_scan_excl<BLOCK>((uint32_t)v, c, total);   // two's complement sums are fine
+                if (s2 < S) {
+                    if (carry + (int)ex + v > 0) flags |= PT_SPAN_COMMENT;
+                    SegFlags[s2] = flags; SegLink[s2] = link;
+                }
                 carry += (int)total;
             }
         }
-        __syncthreads();
 
-        // ---- H: comment presence pieces (per comment id, LWW by opId) in visible space; comment-induced span heads ----
+        // ---- H: comment presence pieces (per comment id an LWW channel, peritext.ts:314-322 folded in opId order) ----------
+        // comment ops sorted by (id, op index) by counting; a piece = elementary interval of one id where an add wins
         const uint32_t HW = nvis / 32 + 1;
         uint32_t* CHead = A.alloc<uint32_t>(HW + 1);
-        uint32_t* PcId = A.alloc<uint32_t>(2 * Mc + 1);
+        uint32_t* CId = A.alloc<uint32_t>(Mc + 1);        // sorted by (id, k)
+        Idx* CK = A.alloc<Idx>(Mc + 1);                   // mark op index
+        Idx* CG0 = A.alloc<Idx>(Mc + 1);                  // first sorted position of the op's id group
+        Idx* CGn = A.alloc<Idx>(Mc + 1);                  // group size
         Idx* PcA = A.alloc<Idx>(2 * Mc + 1);
-        Idx* PcB = A.alloc<Idx>(2 * Mc + 1);      // PcA == PcB: dead piece
+        Idx* PcB = A.alloc<Idx>(2 * Mc + 1);              // PcA == PcB: dead piece
         fill<uint32_t, BLOCK>(CHead, HW + 1, 0u);
+        for (uint32_t ci = tid; ci < Mc; ci += BLOCK) {
+            const uint32_t k = CompactC[ci], id = MAttr[k];
+            uint32_t less = 0, eqBefore = 0, eqTotal = 0;
+            for (uint32_t cj = 0; cj < Mc; cj++) {
+                const uint32_t j = CompactC[cj], idj = MAttr[j];
+                less += (idj < id || (idj == id && j < k)) ? 1u : 0u;
+                eqBefore += (idj == id && j < k) ? 1u : 0u;
+                eqTotal += (idj == id) ? 1u : 0u;
+            }
+            CId[less] = id; CK[less] = (Idx)k; CG0[less] = (Idx)(less - eqBefore); CGn[less] = (Idx)eqTotal;
+        }
         __syncthreads();
         for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
-            uint32_t ci = e >> 1, which = e & 1u, k = CompactC[ci];
-            uint32_t id = mk[k].attr;
-            uint32_t x = which ? (uint32_t)IvB[k] : (uint32_t)IvA[k];
-            uint32_t xv = which ? (uint32_t)IvVB[k] : (uint32_t)IvVA[k];
+            const uint32_t ci = e >> 1, which = e & 1u, k = CK[ci];
+            const uint32_t g0 = CG0[ci], g1 = g0 + (uint32_t)CGn[ci];
+            const uint32_t x = which ? (uint32_t)IvB[k] : (uint32_t)IvA[k];
+            const uint32_t xv = which ? (uint32_t)IvVB[k] : (uint32_t)IvVA[k];
             bool dup = false; uint32_t nextEnd = 0xFFFFFFFFu, nextV = 0;
-            for (uint32_t cj = 0; cj < Mc; cj++) {
-                uint32_t j = CompactC[cj];
-                if (mk[j].attr != id) continue;
-                uint32_t ja = IvA[j], jb = IvB[j];
+            for (uint32_t cj = g0; cj < g1; cj++) {
+                const uint32_t j = CK[cj];
+                const uint32_t ja = IvA[j], jb = IvB[j];
                 if (ja == x && (cj < ci || (cj == ci && 0u < which))) dup = true;
                 if (jb == x && (cj < ci || (cj == ci && 1u < which))) dup = true;
                 if (ja > x && ja < nextEnd) { nextEnd = ja; nextV = IvVA[j]; }
@@ -592,26 +606,25 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             uint32_t va = 0, vb = 0;
             if (!dup && nextEnd != 0xFFFFFFFFu) {
                 uint32_t best = 0; bool bestAdd = false;
-                for (uint32_t cj = 0; cj < Mc; cj++) {
-                    uint32_t j = CompactC[cj];
-                    if (mk[j].attr != id) continue;
+                for (uint32_t cj = g0; cj < g1; cj++) {
+                    const uint32_t j = CK[cj];
                     if ((uint32_t)IvA[j] <= x && nextEnd <= (uint32_t)IvB[j]) {
-                        uint32_t rk = (uint32_t)MRank[j] + 1u;
-                        if (rk > best) { best = rk; bestAdd = (mk[j].kind & 1u) == 0; }
+                        const uint32_t rk = (uint32_t)MRank[j] + 1u;
+                        if (rk > best) { best = rk; bestAdd = (MKind[j] & 1u) == 0; }
                     }
                 }
                 if (best && bestAdd) { va = xv; vb = nextV; if (va >= vb) { va = 0; vb = 0; } }
             }
-            PcId[e] = id; PcA[e] = (Idx)va; PcB[e] = (Idx)vb;
+            PcA[e] = (Idx)va; PcB[e] = (Idx)vb;
         }
         __syncthreads();
         for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
-            uint32_t va = PcA[e], vb = PcB[e], id = PcId[e];
+            const uint32_t va = PcA[e], vb = PcB[e];
             if (va >= vb) continue;
+            const uint32_t ci = e >> 1, g0 = CG0[ci], g1 = g0 + (uint32_t)CGn[ci];
             bool startTouch = false, endTouch = false;
-            for (uint32_t f = 0; f < 2 * Mc; f++) {
-                if (PcId[f] != id) continue;
-                uint32_t fa = PcA[f], fb = PcB[f];
+            for (uint32_t f = 2 * g0; f < 2 * g1; f++) {
+                const uint32_t fa = PcA[f], fb = PcB[f];
                 if (fa >= fb) continue;
                 if (fb == va) startTouch = true;
                 if (fa == vb) endTouch = true;
@@ -630,26 +643,25 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             VisSeg[visOf(i)] = (Idx)segOf(posOf(i));
         }
         __syncthreads();
+        for (uint32_t base = 0; base < VW * 32; base += BLOCK) {       // head flags: one thread per visible position, ballot -> word
+            const uint32_t v = base + tid;
+            bool h = false;
+            if (v < nvis) {
+                if (v == 0) h = true;
+                else {
+                    const uint32_t s1 = VisSeg[v - 1], s2 = VisSeg[v];
+                    h = ((CHead[v >> 5] >> (v & 31)) & 1u) || (s1 != s2 && (SegFlags[s1] != SegFlags[s2] || SegLink[s1] != SegLink[s2]));
+                }
+            }
+            const uint32_t bits = __ballot_sync(0xffffffffu, h);
+            if (lane == 0 && (v >> 5) < VW) HeadB[v >> 5] = bits;
+        }
+        __syncthreads();
         {
             uint32_t carry = 0;
             for (uint32_t base = 0; base < VW; base += BLOCK) {
-                uint32_t w = base + tid, bits = 0;
-                if (w < VW) {
-                    for (uint32_t b = 0; b < 32; b++) {
-                        uint32_t v = w * 32 + b;
-                        if (v >= nvis) break;
-                        bool h;
-                        if (v == 0) h = true;
-                        else {
-                            uint32_t s1 = VisSeg[v - 1], s2 = VisSeg[v];
-                            h = ((CHead[v >> 5] >> (v & 31)) & 1u) ||
-                                (s1 != s2 && (SegFlags[s1] != SegFlags[s2] || SegLink[s1] != SegLink[s2]));
-                        }
-                        if (h) bits |= 1u << b;
-                    }
-                    HeadB[w] = bits;
-                }
-                uint32_t total, ex = block_scan_excl<BLOCK>(__popc(bits), c, total);
+                uint32_t w = base + tid, total;
+                uint32_t ex = block_scan_excl<BLOCK>(w < VW ? __popc(HeadB[w]) : 0u, c, total);
                 if (w < VW) HeadP[w] = (Idx)(carry + ex);
                 carry += total;
             }
@@ -661,12 +673,15 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             if (w >= VW) return nspans;
             return (uint32_t)HeadP[w] + __popc(HeadB[w] & ((1u << b) - 1u));
         };
-        // comment lists per span: count, reserve pool space, fill, sort
+        // comment lists per span: count, reserve pool space, fill, sort; span start positions for the per-span pass
+        Idx* SpanStart = A.alloc<Idx>(nspans + 1);
         uint32_t* SpanCC = A.alloc<uint32_t>(nspans + 1);
         uint32_t* SpanCO = A.alloc<uint32_t>(nspans + 1);
         uint32_t* SpanCur = A.alloc<uint32_t>(nspans + 1);
         fill<uint32_t, BLOCK>(SpanCC, nspans + 1, 0u);
         fill<uint32_t, BLOCK>(SpanCur, nspans + 1, 0u);
+        for (uint32_t v = tid; v < nvis; v += BLOCK)
+            if ((HeadB[v >> 5] >> (v & 31)) & 1u) SpanStart[headRank(v)] = (Idx)v;
         __syncthreads();
         for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
             uint32_t va = PcA[e], vb = PcB[e];
@@ -699,31 +714,27 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
             uint32_t va = PcA[e], vb = PcB[e];
             if (va >= vb) continue;
+            const uint32_t id = CId[e >> 1];
             for (uint32_t j = headRank(va), j1 = headRank(vb); j < j1; j++)
-                pool[SpanCO[j] + atomicAdd(&SpanCur[j], 1u)] = PcId[e];
+                pool[SpanCO[j] + atomicAdd(&SpanCur[j], 1u)] = id;
         }
         __syncthreads();
         {
             unsigned long long d0 = 0, d1 = 0;
-            for (uint32_t w = tid; w < VW; w += BLOCK) {
-                uint32_t bits = HeadB[w], j = HeadP[w];
-                while (bits) {
-                    uint32_t b = __ffs(bits) - 1; bits &= bits - 1;
-                    uint32_t v = w * 32 + b, s = VisSeg[v];
-                    uint32_t cnt = SpanCC[j];
-                    uint32_t* lst = pool + SpanCO[j];
-                    for (uint32_t x = 1; x < cnt; x++) {                   // insertion sort: ascending comment id
-                        uint32_t key = lst[x]; uint32_t y = x;
-                        while (y > 0 && lst[y - 1] > key) { lst[y] = lst[y - 1]; y--; }
-                        lst[y] = key;
-                    }
-                    pt_span sp; sp.start = v; sp.flags = SegFlags[s] | (cnt << 8); sp.link_attr = SegLink[s];
-                    sp.comment_off = cnt ? (uint32_t)(c.pool_base + SpanCO[j]) : 0u;
-                    span_out[j] = sp;
-                    for (uint32_t x = 0; x < cnt; x++) digest_add(d0, d1, pt_term_comment(j, x, lst[x]));
-                    digest_add(d0, d1, pt_term_span(j, sp.start, sp.flags, sp.link_attr));
-                    j++;
+            for (uint32_t j = tid; j < nspans; j += BLOCK) {                // one thread per span
+                const uint32_t v = SpanStart[j], s2 = VisSeg[v];
+                const uint32_t cnt = SpanCC[j];
+                uint32_t* lst = pool + SpanCO[j];
+                for (uint32_t x = 1; x < cnt; x++) {                        // insertion sort: ascending comment id
+                    uint32_t key = lst[x]; uint32_t y = x;
+                    while (y > 0 && lst[y - 1] > key) { lst[y] = lst[y - 1]; y--; }
+                    lst[y] = key;
                 }
+                pt_span sp; sp.start = v; sp.flags = SegFlags[s2] | (cnt << 8); sp.link_attr = SegLink[s2];
+                sp.comment_off = cnt ? (uint32_t)(c.pool_base + SpanCO[j]) : 0u;
+                span_out[j] = sp;
+                for (uint32_t x = 0; x < cnt; x++) digest_add(d0, d1, pt_term_comment(j, x, lst[x]));
+                digest_add(d0, d1, pt_term_span(j, sp.start, sp.flags, sp.link_attr));
             }
             digest_flush<BLOCK>(c, d0, d1);
         }
