@@ -84,6 +84,7 @@ size_t arena_worst_bytes(uint64_t n, uint64_t m, uint64_t KS) {
         A(3 * (2 * S + 2), 4); A(S + 1, 4); A(S + 1, 4); A(S + 2, 4);              // Tree[3] SegFlags SegLink CDiff
         A(n / 32 + 3, 4); A(Mc + 1, 4); A(Mc + 1, I); A(Mc + 1, I); A(Mc + 1, I);  // CHead CId CK CG0 CGn
         A(2 * Mc + 1, I); A(2 * Mc + 1, I);                                        // PcA PcB
+        A(4 * Mc + 8, 4); A(4 * Mc + 9, 4); A(4 * Mc + 9, I); A(Mc + 1, I);        // HTab HCnt HOff CSlot
         A(n + 1, I); A(n / 32 + 2, 4); A(n / 32 + 2, I);                           // VisSeg HeadB HeadP
         A(nsp + 1, I); A(nsp + 1, 4); A(nsp + 1, 4); A(nsp + 1, 4);                // SpanStart SpanCC SpanCO SpanCur
     }

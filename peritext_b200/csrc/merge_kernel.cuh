@@ -99,17 +99,30 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, BlockCtx<BLOCK>&
     return ea;
 }
 
+extern __shared__ __align__(16) char ptk_smem[];   // dynamic shared memory = the arena's fast region
+
+// SH = true : every array must fit in dynamic shared memory; pointers are derived from the __shared__ symbol so the
+//             compiler emits LDS/STS with 32-bit addresses.  An allocation that does not fit sets `overflow` and the
+//             caller restarts the log in the SH = false instantiation.
+// SH = false: shared memory first, then the per-CTA global slab (generic pointers).
+template <bool SH>
 struct Arena {
-    char* sm; uint32_t sm_cap, sm_used;
+    uint32_t sm_cap, sm_used;
     char* gm; unsigned long long gm_cap, gm_used;
     bool overflow;
     template <class T> __device__ __forceinline__ T* alloc(uint32_t count) {
-        uint32_t bytes = (uint32_t)((count * sizeof(T) + 15u) & ~15u);
-        if (sm_used + bytes <= sm_cap) { T* p = reinterpret_cast<T*>(sm + sm_used); sm_used += bytes; return p; }
+        const uint32_t bytes = (uint32_t)((count * sizeof(T) + 15u) & ~15u);
+        if (SH) {
+            const uint32_t off = sm_used; sm_used += bytes;
+            if (sm_used > sm_cap) { overflow = true; sm_used = off; return reinterpret_cast<T*>(ptk_smem); }
+            return reinterpret_cast<T*>(ptk_smem + off);
+        }
+        if (sm_used + bytes <= sm_cap) { T* p = reinterpret_cast<T*>(ptk_smem + sm_used); sm_used += bytes; return p; }
         if (gm_used + bytes > gm_cap) { overflow = true; return reinterpret_cast<T*>(gm); }
         T* p = reinterpret_cast<T*>(gm + gm_used); gm_used += bytes; return p;
     }
 };
+#define PT_ALLOC(var, T, count) T* var = A.template alloc<T>(count); if (SH && A.overflow) return 1
 
 // fill `count` elements (allocation is padded to 16 B, so whole uint4 stores are safe)
 template <class T, int BLOCK>
@@ -150,8 +163,8 @@ __device__ __forceinline__ unsigned long long node_make(uint32_t nxt, uint32_t w
 // =========================================================================================================
 // The per-log pipeline.  Idx = uint16_t (logs with < 32000 records) or uint32_t.
 // =========================================================================================================
-template <class Idx, int BLOCK>
-__device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>& c, char* smem_arena) {
+template <class Idx, int BLOCK, bool SH>
+__device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>& c) {
     constexpr Idx NONE = (Idx)~(Idx)0;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
 
@@ -164,8 +177,8 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
     pt_span* span_out = P.spans + P.span_off[li];
     pt_log_result* res = P.results + li;
 
-    Arena A;
-    A.sm = smem_arena; A.sm_cap = P.smem_arena_bytes; A.sm_used = 0;
+    Arena<SH> A;
+    A.sm_cap = P.smem_arena_bytes; A.sm_used = 0;
     A.gm = P.slab + (unsigned long long)blockIdx.x * P.slab_bytes; A.gm_cap = P.slab_bytes; A.gm_used = 0; A.overflow = false;
 
     if (tid == 0) { c.status = 0; c.misc[0] = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
@@ -178,16 +191,16 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
     const uint32_t NWr = (n + 31) / 32 + 1;     // words over record indices (+1 zero pad word)
 
     // ---- arrays that live to the end (allocation order = smem priority) --------------------------------------
-    Idx* T = A.alloc<Idx>(KS);                    // A: opId key -> insert record index
-    uint32_t* InsBits = A.alloc<uint32_t>(NWr);   // record is an insert
-    uint32_t* HeadBits = A.alloc<uint32_t>(NWr);  // record starts a run (first: chain-continuation bits)
-    uint32_t* VisBits = A.alloc<uint32_t>(NWr);   // record is a visible element
-    Idx* HeadPre = A.alloc<Idx>(NWr);             // heads in words < w
-    Idx* VisPre = A.alloc<Idx>(NWr);              // visible elements in words < w
+    PT_ALLOC(T, Idx, KS);                    // A: opId key -> insert record index
+    PT_ALLOC(InsBits, uint32_t, NWr);   // record is an insert
+    PT_ALLOC(HeadBits, uint32_t, NWr);  // record starts a run (first: chain-continuation bits)
+    PT_ALLOC(VisBits, uint32_t, NWr);   // record is a visible element
+    PT_ALLOC(HeadPre, Idx, NWr);             // heads in words < w
+    PT_ALLOC(VisPre, Idx, NWr);              // visible elements in words < w
     // byte flags, dead after phase C (released)
     const uint32_t mark_sm = A.sm_used; const unsigned long long mark_gm = A.gm_used;
-    uint8_t* Other = A.alloc<uint8_t>(NWr * 32 + 32);   // element has a child that is not its log successor
-    uint8_t* Del = A.alloc<uint8_t>(NWr * 32 + 32);     // tombstone
+    PT_ALLOC(Other, uint8_t, NWr * 32 + 32);   // element has a child that is not its log successor
+    PT_ALLOC(Del, uint8_t, NWr * 32 + 32);     // tombstone
 
     fill<Idx, BLOCK>(T, KS, NONE);
     fill<uint8_t, BLOCK>(Other, NWr * 32 + 32, (uint8_t)0);
@@ -222,7 +235,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         if (lane == 0 && i < n) { InsBits[i >> 5] = insW; HeadBits[i >> 5] = candW; }
     }
     __syncthreads();
-    if (c.status) { bail(); return; }
+    if (c.status) { bail(); return 0; }
 
     // ---- B: parents of chain heads (-> "has another child" flags), deletes (-> tombstones) ------------------------
     for (uint32_t base = 0; base < n; base += BLOCK) {
@@ -244,7 +257,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         }
     }
     __syncthreads();
-    if (c.status) { bail(); return; }
+    if (c.status) { bail(); return 0; }
 
     // ---- C: runs, bit-parallel: head = insert & (!chain-link | predecessor has another child); visible = insert & !deleted
     uint32_t M, nvis;
@@ -278,7 +291,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
     }
     __syncthreads();
     N = c.misc[0];
-    if (2ull * M + 4 >= (1ull << kNodeNxtBits) || N >= (1u << 22)) { if (tid == 0) c.status = PT_LOG_OVERFLOW; __syncthreads(); bail(); return; }
+    if (2ull * M + 4 >= (1ull << kNodeNxtBits) || N >= (1u << 22)) { if (tid == 0) c.status = PT_LOG_OVERFLOW; __syncthreads(); bail(); return 0; }
 
     auto runOf = [&](uint32_t i) -> uint32_t {     // run id of element record i
         return (uint32_t)HeadPre[i >> 5] + __popc(HeadBits[i >> 5] & (0xFFFFFFFFu >> (31 - (i & 31)))) - 1u;
@@ -289,42 +302,39 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
 
     // ---- D: run tree; children of every node ordered by DESCENDING opId of the run head ---------------------------------
     const uint32_t E = 2 * (M + 1), END = E;
-    unsigned long long* Node = A.alloc<unsigned long long>(E + 1);   // E: Euler-tour nodes (allocated early: hot)
-    Idx* RunHead = A.alloc<Idx>(M + 1);
-    uint32_t* PosBase = A.alloc<uint32_t>(M + 2);   // pos(i) = PosBase[run] + i        (wrap-around arithmetic)
-    uint32_t* VisBase = A.alloc<uint32_t>(M + 2);   // vis(i) = VisBase[run] + visBefore(i)
-    Idx* Prun = A.alloc<Idx>(M + 1);
-    uint32_t* Key = A.alloc<uint32_t>(M + 1);
+    PT_ALLOC(Node, unsigned long long, E + 1);   // E: Euler-tour nodes (allocated early: hot)
+    PT_ALLOC(RunHead, Idx, M + 1);
+    PT_ALLOC(PosBase, uint32_t, M + 2);   // pos(i) = PosBase[run] + i        (wrap-around arithmetic)
+    PT_ALLOC(VisBase, uint32_t, M + 2);   // vis(i) = VisBase[run] + visBefore(i)
+    PT_ALLOC(Prun, Idx, M + 1);
+    PT_ALLOC(Key, uint32_t, M + 1);
     uint32_t* GrpCnt = VisBase;                     // children per node (node M = HEAD); dead before VisBase is written
     uint32_t* GrpCur = PosBase;                     // fill cursors; dead before PosBase is written
-    Idx* GrpOff = A.alloc<Idx>(M + 2);
-    Idx* Unsorted = A.alloc<Idx>(M + 1);
-    Idx* Sorted = A.alloc<Idx>(M + 1);
-    Idx* SPos = A.alloc<Idx>(M + 1);
+    PT_ALLOC(GrpOff, Idx, M + 2);
+    PT_ALLOC(Unsorted, Idx, M + 1);
+    PT_ALLOC(Sorted, Idx, M + 1);
+    PT_ALLOC(SPos, Idx, M + 1);
     fill<uint32_t, BLOCK>(GrpCnt, M + 2, 0u);
     fill<uint32_t, BLOCK>(GrpCur, M + 2, 0u);
     __syncthreads();
-    for (uint32_t w = tid; w < NWr; w += BLOCK) {
-        uint32_t hb = HeadBits[w];
-        uint32_t rid = HeadPre[w];
-        while (hb) {
-            const uint32_t b = __ffs(hb) - 1; hb &= hb - 1;
-            const uint32_t i = w * 32 + b;
-            // run = insert records from i up to the next head or non-insert record
-            uint32_t stop = (HeadBits[w] | ~InsBits[w]) & ~(0xFFFFFFFFu >> (31 - b));
-            uint32_t ww = w;
-            while (!stop) { ww++; stop = HeadBits[ww] | ~InsBits[ww]; }     // pad word: InsBits == 0 -> stops
-            const uint32_t end = ww * 32 + (__ffs(stop) - 1);
-            const uint4 rec = ld_rec(ins + i);
-            const uint32_t p = rec.y == 0 ? n : (uint32_t)T[keyOf(rec.y, rec.z >> 16)];
-            const uint32_t q = p == n ? M : runOf(p);
-            RunHead[rid] = (Idx)i;
-            Node[rid] = node_make(0, end - i, visBefore(end) - visBefore(i));   // weights now, successor in phase E
-            Prun[rid] = (Idx)q;
-            Key[rid] = keyOf(rec.x, rec.z & 0xFFFFu);
-            atomicAdd(&GrpCnt[q], 1u);
-            rid++;
-        }
+    for (uint32_t i = tid; i < n; i += BLOCK) {        // one thread per record; run heads do the work
+        const uint32_t w = i >> 5, b = i & 31;
+        const uint32_t hw = HeadBits[w];
+        if (!((hw >> b) & 1u)) continue;
+        const uint32_t rid = (uint32_t)HeadPre[w] + __popc(hw & ((1u << b) - 1u));
+        // run = insert records from i up to the next head or non-insert record
+        uint32_t stop = (hw | ~InsBits[w]) & ~(0xFFFFFFFFu >> (31 - b));
+        uint32_t ww = w;
+        while (!stop) { ww++; stop = HeadBits[ww] | ~InsBits[ww]; }     // pad word: InsBits == 0 -> stops
+        const uint32_t end = ww * 32 + (__ffs(stop) - 1);
+        const uint4 rec = ld_rec(ins + i);
+        const uint32_t p = rec.y == 0 ? n : (uint32_t)T[keyOf(rec.y, rec.z >> 16)];
+        const uint32_t q = p == n ? M : runOf(p);
+        RunHead[rid] = (Idx)i;
+        Node[rid] = node_make(0, end - i, visBefore(end) - visBefore(i));   // weights now, successor in phase E
+        Prun[rid] = (Idx)q;
+        Key[rid] = keyOf(rec.x, rec.z & 0xFFFFu);
+        atomicAdd(&GrpCnt[q], 1u);
     }
     __syncthreads();
     {
@@ -429,18 +439,18 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         // G1: rank mark ops by opId: bitmap over the key space + prefix popcount (a counting sort with unique keys)
         const uint32_t NWp = (N + 32) / 32 + 1;          // words over sequence positions 0..N
         const uint32_t KW = (KS + 31) / 32;
-        uint32_t* KBits = A.alloc<uint32_t>(KW + 1);
-        Idx* KPre = A.alloc<Idx>(KW + 1);
-        Idx* ByRank = A.alloc<Idx>(m + 1);
-        Idx* MRank = A.alloc<Idx>(m + 1);
-        Idx* IvA = A.alloc<Idx>(m + 1);         // element interval [a,b) per mark op; a == b: covers nothing
-        Idx* IvB = A.alloc<Idx>(m + 1);
-        Idx* IvVA = A.alloc<Idx>(m + 1);        // visible rank of positions a and b
-        Idx* IvVB = A.alloc<Idx>(m + 1);
-        uint8_t* MKind = A.alloc<uint8_t>(m + 1);   // pt_mark_rec.kind (bit0 remove, bits2:1 type)
-        uint32_t* MAttr = A.alloc<uint32_t>(m + 1);
-        uint32_t* BndBits = A.alloc<uint32_t>(NWp + 1);
-        Idx* SegPre = A.alloc<Idx>(NWp + 1);
+        PT_ALLOC(KBits, uint32_t, KW + 1);
+        PT_ALLOC(KPre, Idx, KW + 1);
+        PT_ALLOC(ByRank, Idx, m + 1);
+        PT_ALLOC(MRank, Idx, m + 1);
+        PT_ALLOC(IvA, Idx, m + 1);         // element interval [a,b) per mark op; a == b: covers nothing
+        PT_ALLOC(IvB, Idx, m + 1);
+        PT_ALLOC(IvVA, Idx, m + 1);        // visible rank of positions a and b
+        PT_ALLOC(IvVB, Idx, m + 1);
+        PT_ALLOC(MKind, uint8_t, m + 1);   // pt_mark_rec.kind (bit0 remove, bits2:1 type)
+        PT_ALLOC(MAttr, uint32_t, m + 1);
+        PT_ALLOC(BndBits, uint32_t, NWp + 1);
+        PT_ALLOC(SegPre, Idx, NWp + 1);
         fill<uint32_t, BLOCK>(KBits, KW + 1, 0u);
         fill<uint32_t, BLOCK>(BndBits, NWp + 1, 0u);
         if (tid == 0) { c.misc[1] = 0; }
@@ -454,7 +464,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             if (T[key] != NONE) fail(PT_LOG_BAD_OPID);
         }
         __syncthreads();
-        if (c.status) { bail(); return; }
+        if (c.status) { bail(); return 0; }
         {
             uint32_t carry = 0;
             for (uint32_t base = 0; base < KW; base += BLOCK) {
@@ -466,7 +476,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         }
         __syncthreads();
         // G2: boundary slots -> element intervals; comment ops are compacted on the side
-        uint32_t* CompactC = A.alloc<uint32_t>(m + 1);     // indices of non-empty comment ops
+        PT_ALLOC(CompactC, uint32_t, m + 1);     // indices of non-empty comment ops
         for (uint32_t k = tid; k < m; k += BLOCK) {
             const uint4* q = reinterpret_cast<const uint4*>(mk + k);
             const uint4 r0 = __ldg(q), r1 = __ldg(q + 1);
@@ -520,10 +530,10 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         };
         // G3: stabbing max per LWW type: three iterative segment trees over segment ids (range atomicMax, point query)
         const uint32_t TS = 2 * S + 2;
-        uint32_t* Tree = A.alloc<uint32_t>(3 * TS);      // [strong | em | link]
-        uint32_t* SegFlags = A.alloc<uint32_t>(S + 1);
-        uint32_t* SegLink = A.alloc<uint32_t>(S + 1);
-        int* CDiff = A.alloc<int>(S + 2);
+        PT_ALLOC(Tree, uint32_t, 3 * TS);      // [strong | em | link]
+        PT_ALLOC(SegFlags, uint32_t, S + 1);
+        PT_ALLOC(SegLink, uint32_t, S + 1);
+        PT_ALLOC(CDiff, int, S + 2);
         fill<uint32_t, BLOCK>(Tree, 3 * TS, 0u);
         fill<int, BLOCK>(CDiff, S + 2, 0);
         __syncthreads();
@@ -569,24 +579,50 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         // ---- H: comment presence pieces (per comment id an LWW channel, peritext.ts:314-322 folded in opId order) ----------
         // comment ops sorted by (id, op index) by counting; a piece = elementary interval of one id where an add wins
         const uint32_t HW = nvis / 32 + 1;
-        uint32_t* CHead = A.alloc<uint32_t>(HW + 1);
-        uint32_t* CId = A.alloc<uint32_t>(Mc + 1);        // sorted by (id, k)
-        Idx* CK = A.alloc<Idx>(Mc + 1);                   // mark op index
-        Idx* CG0 = A.alloc<Idx>(Mc + 1);                  // first sorted position of the op's id group
-        Idx* CGn = A.alloc<Idx>(Mc + 1);                  // group size
-        Idx* PcA = A.alloc<Idx>(2 * Mc + 1);
-        Idx* PcB = A.alloc<Idx>(2 * Mc + 1);              // PcA == PcB: dead piece
+        PT_ALLOC(CHead, uint32_t, HW + 1);
+        PT_ALLOC(CId, uint32_t, Mc + 1);        // sorted by (id, k)
+        PT_ALLOC(CK, Idx, Mc + 1);                   // mark op index
+        PT_ALLOC(CG0, Idx, Mc + 1);                  // first sorted position of the op's id group
+        PT_ALLOC(CGn, Idx, Mc + 1);                  // group size
+        PT_ALLOC(PcA, Idx, 2 * Mc + 1);
+        PT_ALLOC(PcB, Idx, 2 * Mc + 1);              // PcA == PcB: dead piece
+        // group the comment ops by id: open-addressing hash of the ids, bucket counts, scan, fill (O(Mc))
+        uint32_t Hbits = 1; while ((1u << Hbits) < 2 * Mc + 2) Hbits++;
+        const uint32_t H = 1u << Hbits;
+        PT_ALLOC(HTab, uint32_t, H);                      // id + 1 (0 = empty); later the fill cursor
+        PT_ALLOC(HCnt, uint32_t, H + 1);
+        PT_ALLOC(HOff, Idx, H + 1);
+        PT_ALLOC(CSlot, Idx, Mc + 1);
         fill<uint32_t, BLOCK>(CHead, HW + 1, 0u);
+        fill<uint32_t, BLOCK>(HTab, H, 0u);
+        fill<uint32_t, BLOCK>(HCnt, H + 1, 0u);
+        __syncthreads();
         for (uint32_t ci = tid; ci < Mc; ci += BLOCK) {
-            const uint32_t k = CompactC[ci], id = MAttr[k];
-            uint32_t less = 0, eqBefore = 0, eqTotal = 0;
-            for (uint32_t cj = 0; cj < Mc; cj++) {
-                const uint32_t j = CompactC[cj], idj = MAttr[j];
-                less += (idj < id || (idj == id && j < k)) ? 1u : 0u;
-                eqBefore += (idj == id && j < k) ? 1u : 0u;
-                eqTotal += (idj == id) ? 1u : 0u;
+            const uint32_t id = MAttr[CompactC[ci]];
+            uint32_t slot = (id * 2654435761u) >> (32 - Hbits);
+            for (;;) {
+                const uint32_t old = atomicCAS(&HTab[slot], 0u, id + 1u);
+                if (old == 0u || old == id + 1u) break;
+                slot = (slot + 1) & (H - 1);
             }
-            CId[less] = id; CK[less] = (Idx)k; CG0[less] = (Idx)(less - eqBefore); CGn[less] = (Idx)eqTotal;
+            CSlot[ci] = (Idx)slot;
+            atomicAdd(&HCnt[slot], 1u);
+        }
+        __syncthreads();
+        {
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < H; base += BLOCK) {
+                uint32_t q = base + tid, total;
+                uint32_t ex = block_scan_excl<BLOCK>(q < H ? HCnt[q] : 0u, c, total);
+                if (q < H) HOff[q] = (Idx)(carry + ex);
+                carry += total;
+            }
+        }
+        __syncthreads();
+        for (uint32_t ci = tid; ci < Mc; ci += BLOCK) {
+            const uint32_t k = CompactC[ci], id = MAttr[k], slot = CSlot[ci];
+            const uint32_t pos = (uint32_t)HOff[slot] + (atomicAdd(&HTab[slot], 1u) - (id + 1u));
+            CId[pos] = id; CK[pos] = (Idx)k; CG0[pos] = HOff[slot]; CGn[pos] = (Idx)HCnt[slot];
         }
         __syncthreads();
         for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
@@ -634,10 +670,10 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         }
 
         // ---- I: spans ---------------------------------------------------------------------------------------------------
-        Idx* VisSeg = A.alloc<Idx>(nvis + 1);
+        PT_ALLOC(VisSeg, Idx, nvis + 1);
         const uint32_t VW = (nvis + 31) / 32;
-        uint32_t* HeadB = A.alloc<uint32_t>(VW + 1);
-        Idx* HeadP = A.alloc<Idx>(VW + 1);
+        PT_ALLOC(HeadB, uint32_t, VW + 1);
+        PT_ALLOC(HeadP, Idx, VW + 1);
         for (uint32_t i = tid; i < n; i += BLOCK) {
             if (!isVis(i)) continue;
             VisSeg[visOf(i)] = (Idx)segOf(posOf(i));
@@ -674,10 +710,10 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             return (uint32_t)HeadP[w] + __popc(HeadB[w] & ((1u << b) - 1u));
         };
         // comment lists per span: count, reserve pool space, fill, sort; span start positions for the per-span pass
-        Idx* SpanStart = A.alloc<Idx>(nspans + 1);
-        uint32_t* SpanCC = A.alloc<uint32_t>(nspans + 1);
-        uint32_t* SpanCO = A.alloc<uint32_t>(nspans + 1);
-        uint32_t* SpanCur = A.alloc<uint32_t>(nspans + 1);
+        PT_ALLOC(SpanStart, Idx, nspans + 1);
+        PT_ALLOC(SpanCC, uint32_t, nspans + 1);
+        PT_ALLOC(SpanCO, uint32_t, nspans + 1);
+        PT_ALLOC(SpanCur, uint32_t, nspans + 1);
         fill<uint32_t, BLOCK>(SpanCC, nspans + 1, 0u);
         fill<uint32_t, BLOCK>(SpanCur, nspans + 1, 0u);
         for (uint32_t v = tid; v < nvis; v += BLOCK)
@@ -709,7 +745,7 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
             c.pool_base = base;
         }
         __syncthreads();
-        if (c.status) { bail(); return; }
+        if (c.status) { bail(); return 0; }
         uint32_t* pool = P.comment_pool + c.pool_base;
         for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
             uint32_t va = PcA[e], vb = PcB[e];
@@ -750,13 +786,13 @@ __device__ void merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>
         *res = r;
     }
     __syncthreads();
+    return 0;
 }
 
 // Persistent CTAs pull logs from the bin's work queue; the next log's records are prefetched into L2 while the
 // current one is processed.
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : BLOCK == 128 ? 7 : 1)) merge_logs_kernel(const BatchParams P) {
-    extern __shared__ __align__(16) char smem_arena[];
     __shared__ BlockCtx<BLOCK> ctx;
     if (threadIdx.x == 0) ctx.work_next = atomicAdd(P.work_counter, 1u);
     __syncthreads();
@@ -776,8 +812,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : 
         const uint32_t li = P.order[w];
         const pt_log_desc& L = P.desc[li];
         const bool small = L.n_insdel < 32000u && L.n_mark < 32000u;
-        if (small) merge_one_log<uint16_t, BLOCK>(P, li, ctx, smem_arena);
-        else merge_one_log<uint32_t, BLOCK>(P, li, ctx, smem_arena);
+        // optimistic: everything in shared memory (LDS/STS); restart with the spill-capable variant if it does not fit
+        if (small) { if (merge_one_log<uint16_t, BLOCK, true>(P, li, ctx)) { __syncthreads(); merge_one_log<uint16_t, BLOCK, false>(P, li, ctx); } }
+        else { if (merge_one_log<uint32_t, BLOCK, true>(P, li, ctx)) { __syncthreads(); merge_one_log<uint32_t, BLOCK, false>(P, li, ctx); } }
     }
 }
 
