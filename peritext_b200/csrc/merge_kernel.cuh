@@ -302,10 +302,34 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
 
     // ---- D: run tree; children of every node ordered by DESCENDING opId of the run head ---------------------------------
     const uint32_t E = 2 * (M + 1), END = E;
-    PT_ALLOC(Node, unsigned long long, E + 1);   // E: Euler-tour nodes (allocated early: hot)
-    PT_ALLOC(RunHead, Idx, M + 1);
+    if (SH) {   // will everything fit in shared memory?  (upper bound on the peak of the stack-like arena; avoids wasted attempts)
+        auto al = [](unsigned long long b) -> unsigned long long { return (b + 15ull) & ~15ull; };
+        const unsigned long long I = sizeof(Idx);
+        const unsigned long long base = (unsigned long long)A.sm_used + 2 * al((M + 2) * 4ull);
+        unsigned long long peak = base + al((E + 1) * 8ull) + 5 * al((M + 1) * I) + al((M + 1) * 4ull) + al((M + 2) * I);
+        if (m) {
+            const unsigned long long NWp_ = (N + 32) / 32 + 1, KW_ = (KS + 31) / 32;
+            const unsigned long long Sb = (2ull * m + 2 < (unsigned long long)N + 2 ? 2ull * m + 2 : (unsigned long long)N + 2) + 1;
+            const unsigned long long Mcb = m, Hb = 4 * Mcb + 8, VWb = (nvis + 31) / 32, nsp = nvis < 2ull * m + 1 ? nvis : 2ull * m + 1;
+            const unsigned long long Pm = base + 6 * al((m + 1) * I) + al(m + 1) + 2 * al((m + 1) * 4ull) + al((NWp_ + 1) * 4) + al((NWp_ + 1) * I);
+            const unsigned long long pG2 = Pm + al((KW_ + 1) * 4) + al((KW_ + 1) * I);
+            const unsigned long long Q = Pm + 2 * al((Sb + 1) * 4);
+            const unsigned long long pG3 = Q + al(3 * (2 * Sb + 2) * 4) + al((Sb + 2) * 4);
+            const unsigned long long Rr = Q + al((nvis / 32 + 2) * 4ull) + al((Mcb + 1) * 4) + 3 * al((Mcb + 1) * I) + 2 * al((2 * Mcb + 1) * I);
+            const unsigned long long pH = Rr + 2 * al((Hb + 1) * 4) + al((Hb + 1) * I) + al((Mcb + 1) * I);
+            const unsigned long long pI = Rr + al((nvis + 1ull) * I) + al((VWb + 1) * 4) + al((VWb + 1) * I) + al((nsp + 1) * I) + 3 * al((nsp + 1) * 4);
+            if (pG2 > peak) peak = pG2;
+            if (pG3 > peak) peak = pG3;
+            if (pH > peak) peak = pH;
+            if (pI > peak) peak = pI;
+        }
+        if (peak > A.sm_cap) return 1;
+    }
     PT_ALLOC(PosBase, uint32_t, M + 2);   // pos(i) = PosBase[run] + i        (wrap-around arithmetic)
     PT_ALLOC(VisBase, uint32_t, M + 2);   // vis(i) = VisBase[run] + visBefore(i)
+    const uint32_t mark2_sm = A.sm_used; const unsigned long long mark2_gm = A.gm_used;   // run-tree temporaries, released after E
+    PT_ALLOC(Node, unsigned long long, E + 1);   // E: Euler-tour nodes
+    PT_ALLOC(RunHead, Idx, M + 1);
     PT_ALLOC(Prun, Idx, M + 1);
     PT_ALLOC(Key, uint32_t, M + 1);
     uint32_t* GrpCnt = VisBase;                     // children per node (node M = HEAD); dead before VisBase is written
@@ -403,6 +427,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         VisBase[r] = (nvis - sufVis) - visBefore(h);
     }
     __syncthreads();
+    A.sm_used = mark2_sm; A.gm_used = mark2_gm;     // release the run-tree temporaries
     auto posOf = [&](uint32_t i) -> uint32_t { return PosBase[runOf(i)] + i; };                    // sequence position of element record i
     auto visOf = [&](uint32_t i) -> uint32_t { return VisBase[runOf(i)] + visBefore(i); };         // visible elements before it in the sequence
     auto isVis = [&](uint32_t i) -> bool { return (VisBits[i >> 5] >> (i & 31)) & 1u; };
@@ -439,8 +464,6 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         // G1: rank mark ops by opId: bitmap over the key space + prefix popcount (a counting sort with unique keys)
         const uint32_t NWp = (N + 32) / 32 + 1;          // words over sequence positions 0..N
         const uint32_t KW = (KS + 31) / 32;
-        PT_ALLOC(KBits, uint32_t, KW + 1);
-        PT_ALLOC(KPre, Idx, KW + 1);
         PT_ALLOC(ByRank, Idx, m + 1);
         PT_ALLOC(MRank, Idx, m + 1);
         PT_ALLOC(IvA, Idx, m + 1);         // element interval [a,b) per mark op; a == b: covers nothing
@@ -449,8 +472,12 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         PT_ALLOC(IvVB, Idx, m + 1);
         PT_ALLOC(MKind, uint8_t, m + 1);   // pt_mark_rec.kind (bit0 remove, bits2:1 type)
         PT_ALLOC(MAttr, uint32_t, m + 1);
+        PT_ALLOC(CompactC, uint32_t, m + 1);     // indices of non-empty comment ops
         PT_ALLOC(BndBits, uint32_t, NWp + 1);
         PT_ALLOC(SegPre, Idx, NWp + 1);
+        const uint32_t mark3_sm = A.sm_used; const unsigned long long mark3_gm = A.gm_used;
+        PT_ALLOC(KBits, uint32_t, KW + 1);       // temporaries of G1/G2
+        PT_ALLOC(KPre, Idx, KW + 1);
         fill<uint32_t, BLOCK>(KBits, KW + 1, 0u);
         fill<uint32_t, BLOCK>(BndBits, NWp + 1, 0u);
         if (tid == 0) { c.misc[1] = 0; }
@@ -476,7 +503,6 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         }
         __syncthreads();
         // G2: boundary slots -> element intervals; comment ops are compacted on the side
-        PT_ALLOC(CompactC, uint32_t, m + 1);     // indices of non-empty comment ops
         for (uint32_t k = tid; k < m; k += BLOCK) {
             const uint4* q = reinterpret_cast<const uint4*>(mk + k);
             const uint4 r0 = __ldg(q), r1 = __ldg(q + 1);
@@ -511,6 +537,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             }
         }
         __syncthreads();
+        A.sm_used = mark3_sm; A.gm_used = mark3_gm;     // release KBits / KPre
         const uint32_t Mc = c.misc[1];
         uint32_t S;   // number of segment ids: seg(x) in [0, S)
         {
@@ -530,9 +557,10 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         };
         // G3: stabbing max per LWW type: three iterative segment trees over segment ids (range atomicMax, point query)
         const uint32_t TS = 2 * S + 2;
-        PT_ALLOC(Tree, uint32_t, 3 * TS);      // [strong | em | link]
         PT_ALLOC(SegFlags, uint32_t, S + 1);
         PT_ALLOC(SegLink, uint32_t, S + 1);
+        const uint32_t mark4_sm = A.sm_used; const unsigned long long mark4_gm = A.gm_used;
+        PT_ALLOC(Tree, uint32_t, 3 * TS);      // [strong | em | link]   (temporaries of G3)
         PT_ALLOC(CDiff, int, S + 2);
         fill<uint32_t, BLOCK>(Tree, 3 * TS, 0u);
         fill<int, BLOCK>(CDiff, S + 2, 0);
@@ -575,6 +603,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
                 carry += (int)total;
             }
         }
+        A.sm_used = mark4_sm; A.gm_used = mark4_gm;     // release Tree / CDiff (the scan above ended with a barrier)
 
         // ---- H: comment presence pieces (per comment id an LWW channel, peritext.ts:314-322 folded in opId order) ----------
         // comment ops sorted by (id, op index) by counting; a piece = elementary interval of one id where an add wins
@@ -589,7 +618,8 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         // group the comment ops by id: open-addressing hash of the ids, bucket counts, scan, fill (O(Mc))
         uint32_t Hbits = 1; while ((1u << Hbits) < 2 * Mc + 2) Hbits++;
         const uint32_t H = 1u << Hbits;
-        PT_ALLOC(HTab, uint32_t, H);                      // id + 1 (0 = empty); later the fill cursor
+        const uint32_t mark5_sm = A.sm_used; const unsigned long long mark5_gm = A.gm_used;
+        PT_ALLOC(HTab, uint32_t, H);                      // id + 1 (0 = empty); later the fill cursor   (temporaries)
         PT_ALLOC(HCnt, uint32_t, H + 1);
         PT_ALLOC(HOff, Idx, H + 1);
         PT_ALLOC(CSlot, Idx, Mc + 1);
@@ -625,6 +655,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             CId[pos] = id; CK[pos] = (Idx)k; CG0[pos] = HOff[slot]; CGn[pos] = (Idx)HCnt[slot];
         }
         __syncthreads();
+        A.sm_used = mark5_sm; A.gm_used = mark5_gm;     // release the hash temporaries
         for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
             const uint32_t ci = e >> 1, which = e & 1u, k = CK[ci];
             const uint32_t g0 = CG0[ci], g1 = g0 + (uint32_t)CGn[ci];
