@@ -288,7 +288,7 @@ def main():
                        "parallelism": f"doc-sharded x{world}", "l2": "input (%.0f MB) larger than the 126 MB L2; no flush needed" % (in_bytes / 1e6)
                        if in_bytes > 130e6 else "input smaller than L2 (steps may hit L2)",
                        "generator_s": round(gen_s, 2), "all_status_ok": ok, "replicas_converged": converged,
-                       "docs_per_sec": (n_logs * world) / (ms_per_step / 1e3)},
+                       "docs_per_sec": (n_logs * world) / (ms_per_step / 1e3), "kernel_paths": eng.stats()},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "ptk::merge_logs_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

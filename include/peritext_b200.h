@@ -196,6 +196,10 @@ int pt_batch_device_results(pt_batch*, void** dev_ptr, uint32_t* n_logs);
 /* Number of kernel launches the handle has enqueued so far (bench `gpu_launches`). */
 uint64_t pt_batch_launch_count(const pt_batch*);
 
+/* Diagnostics of the last merge: out[0] = logs materialised entirely in shared memory, out[1] = logs that were
+ * restarted on the spill-capable path (working set larger than the bin's shared-memory budget). Synchronises. */
+int pt_batch_stats(pt_batch*, uint64_t out[4]);
+
 /* Time of the last pt_batch_merge on the device, in milliseconds (CUDA events recorded on the
  * handle's stream around the launches); <0 if not available. Synchronises. */
 float pt_batch_last_merge_ms(pt_batch*);

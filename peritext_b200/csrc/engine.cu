@@ -108,7 +108,7 @@ struct pt_batch {
     uint32_t bin_first[kNumBins + 1] = {0};
     size_t bin_slab[kNumBins] = {0};
     // device
-    DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_pool_used, d_slab;
+    DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_pool_used, d_slab, d_stats;
     const pt_insdel_rec* dp_insdel = nullptr;
     const pt_mark_rec* dp_marks = nullptr;
     // pinned host
@@ -133,7 +133,7 @@ void load_bins_from_env() {
     while (k < kNumBins && *p) {
         unsigned long a, bl, sm, ct; int used = 0;
         if (sscanf(p, "%lu:%lu:%lu:%lu%n", &a, &bl, &sm, &ct, &used) != 4) return;
-        if (bl != 128 && bl != 256 && bl != 512 && bl != 1024) return;
+        if (bl != 32 && bl != 64 && bl != 128 && bl != 256 && bl != 512 && bl != 1024) return;
         tmp[k++] = BinCfg{(uint32_t)a, (int)bl, (uint32_t)(sm * 1024), (int)ct};
         p += used; if (*p == ',') p++;
     }
@@ -193,6 +193,7 @@ int alloc_and_upload_plan(pt_batch* b) {
     if ((rc = b->d_spans.reserve(std::max<uint64_t>(1, b->n_span) * sizeof(pt_span)))) return rc;
     if ((rc = b->d_pool.reserve(std::max<uint64_t>(1, b->pool_cap) * 4))) return rc;
     if ((rc = b->d_pool_used.reserve(8))) return rc;
+    if ((rc = b->d_stats.reserve(64))) return rc;
     size_t slab_total = 0;
     for (int k = 0; k < kNumBins; k++) {
         uint32_t cnt = b->bin_first[k + 1] - b->bin_first[k];
@@ -236,6 +237,8 @@ int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P) {
 int launch_bin(pt_batch* b, int k, const ptk::BatchParams& P) {
     if (b->bin_first[k + 1] == b->bin_first[k]) return PT_OK;
     switch (kBins[k].block) {
+        case 32: return launch_bin_t<32>(b, k, P);
+        case 64: return launch_bin_t<64>(b, k, P);
         case 128: return launch_bin_t<128>(b, k, P);
         case 256: return launch_bin_t<256>(b, k, P);
         case 512: return launch_bin_t<512>(b, k, P);
@@ -305,6 +308,7 @@ int pt_batch_merge(pt_batch* b) {
     PT_CUDA(cudaEventRecord(b->ev0, b->stream));
     PT_CUDA(cudaMemsetAsync(b->d_counters.p, 0, kNumBins * 4, b->stream));
     PT_CUDA(cudaMemsetAsync(b->d_pool_used.p, 0, 8, b->stream));
+    PT_CUDA(cudaMemsetAsync(b->d_stats.p, 0, 64, b->stream));
     ptk::BatchParams P{};
     P.desc = (const pt_log_desc*)b->d_desc.p;
     P.insdel = b->dp_insdel; P.marks = b->dp_marks;
@@ -313,6 +317,7 @@ int pt_batch_merge(pt_batch* b) {
     P.text = (uint32_t*)b->d_text.p; P.spans = (pt_span*)b->d_spans.p;
     P.comment_pool = (uint32_t*)b->d_pool.p; P.comment_used = (unsigned long long*)b->d_pool_used.p; P.comment_cap = b->pool_cap;
     P.slab = (char*)b->d_slab.p;
+    P.stats = (unsigned long long*)b->d_stats.p;
     int rc;
     // largest logs first: the long-running CTAs start earliest
     for (int k = kNumBins - 1; k >= 0; k--) if ((rc = launch_bin(b, k, P))) return rc;
@@ -390,12 +395,22 @@ int pt_batch_device_results(pt_batch* b, void** dev_ptr, uint32_t* n_logs) {
 
 uint64_t pt_batch_launch_count(const pt_batch* b) { return b ? b->launches : 0; }
 
+int pt_batch_stats(pt_batch* b, uint64_t out[4]) {
+    if (!b || !out) return PT_ERR_INVALID;
+    if (!b->merged) return PT_ERR_STATE;
+    unsigned long long h[8] = {0};
+    PT_CUDA(cudaMemcpyAsync(h, b->d_stats.p, 32, cudaMemcpyDeviceToHost, b->stream));
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < 4; i++) out[i] = h[i];
+    return PT_OK;
+}
+
 void pt_batch_destroy(pt_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
-                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_pool_used, &b->d_slab}) d->release();
+                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_pool_used, &b->d_slab, &b->d_stats}) d->release();
     for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc}) h->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);

@@ -44,6 +44,7 @@ struct BatchParams {
     char* slab;                           // spill: slab_bytes per CTA
     unsigned long long slab_bytes;
     uint32_t smem_arena_bytes;            // dynamic shared memory given to the arena
+    unsigned long long* stats;            // [0] logs finished on the shared-only path, [1] restarts on the spill path
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -823,7 +824,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
 // Persistent CTAs pull logs from the bin's work queue; the next log's records are prefetched into L2 while the
 // current one is processed.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : BLOCK == 128 ? 7 : 1)) merge_logs_kernel(const BatchParams P) {
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : BLOCK == 128 ? 7 : BLOCK == 64 ? 8 : BLOCK == 32 ? 8 : 1)) merge_logs_kernel(const BatchParams P) {
     __shared__ BlockCtx<BLOCK> ctx;
     if (threadIdx.x == 0) ctx.work_next = atomicAdd(P.work_counter, 1u);
     __syncthreads();
@@ -844,8 +845,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : 
         const pt_log_desc& L = P.desc[li];
         const bool small = L.n_insdel < 32000u && L.n_mark < 32000u;
         // optimistic: everything in shared memory (LDS/STS); restart with the spill-capable variant if it does not fit
-        if (small) { if (merge_one_log<uint16_t, BLOCK, true>(P, li, ctx)) { __syncthreads(); merge_one_log<uint16_t, BLOCK, false>(P, li, ctx); } }
-        else { if (merge_one_log<uint32_t, BLOCK, true>(P, li, ctx)) { __syncthreads(); merge_one_log<uint32_t, BLOCK, false>(P, li, ctx); } }
+        int spill;
+        if (small) { spill = merge_one_log<uint16_t, BLOCK, true>(P, li, ctx); if (spill) { __syncthreads(); merge_one_log<uint16_t, BLOCK, false>(P, li, ctx); } }
+        else { spill = merge_one_log<uint32_t, BLOCK, true>(P, li, ctx); if (spill) { __syncthreads(); merge_one_log<uint32_t, BLOCK, false>(P, li, ctx); } }
+        if (threadIdx.x == 0) atomicAdd(&P.stats[spill ? 1 : 0], 1ull);
     }
 }
 

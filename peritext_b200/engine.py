@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libperitext_b200.so")
 _lib = None
 
 EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_adopt_device", "pt_batch_merge", "pt_batch_sync",
-           "pt_batch_download", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count",
+           "pt_batch_download", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count", "pt_batch_stats",
            "pt_batch_last_merge_ms", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
 
 
@@ -59,6 +59,7 @@ def load_library() -> ctypes.CDLL:
     L.pt_batch_download_results.argtypes = [vp, vp, u32]
     L.pt_batch_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u32)]
     L.pt_batch_launch_count.argtypes = [vp]; L.pt_batch_launch_count.restype = u64
+    L.pt_batch_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 4)]
     L.pt_batch_last_merge_ms.argtypes = [vp]; L.pt_batch_last_merge_ms.restype = ctypes.c_float
     L.pt_batch_destroy.argtypes = [vp]; L.pt_batch_destroy.restype = None
     L.pt_strerror.argtypes = [ctypes.c_int]; L.pt_strerror.restype = ctypes.c_char_p
@@ -117,6 +118,11 @@ class BatchEngine:
     @property
     def launch_count(self) -> int:
         return int(self._L.pt_batch_launch_count(self._h))
+
+    def stats(self) -> dict:
+        out = (ctypes.c_uint64 * 4)()
+        _check(self._L.pt_batch_stats(self._h, ctypes.byref(out)), "pt_batch_stats")
+        return {"logs_shared_only": int(out[0]), "logs_spill_restart": int(out[1])}
 
     def device_results_ptr(self) -> int:
         p = ctypes.c_void_p(); n = ctypes.c_uint32()
