@@ -1,8 +1,9 @@
 /* pt_digest.h — definition of the 128-bit per-log digest in pt_log_result.digest.
  *
  * The digest is this engine's stand-in for the fuzz harness's `assert.deepStrictEqual(leftText, rightText)`
- * (reference test/fuzz.ts:278): two replicas converged iff their digests are equal.  It is a commutative
- * sum of position-salted 64-bit mixes so that it can be reduced in any order (warp shuffles, atomics)
+ * (reference test/fuzz.ts:278): two replicas converged iff their digests are equal.  Every covered item
+ * contributes one position-salted 64-bit term t; digest[0] = SUM of the terms (mod 2^64), digest[1] = XOR of
+ * rotl(t, 23).  Both lanes are commutative, so the digest can be reduced in any order (warp shuffles, atomics)
  * and still be deterministic.  Covered: every visible token with its index, every span (index, start,
  * flags incl. comment count, link id) and every comment id with (span index, ordinal).  Pool OFFSETS are
  * not covered (they depend on allocation order).
@@ -34,7 +35,7 @@ PT_HD uint64_t pt_term_comment(uint32_t j, uint32_t k, uint32_t id) {
 PT_HD uint64_t pt_term_counts(uint32_t n_visible, uint32_t n_spans) {
     return pt_mix64((((uint64_t)n_visible << 32) | n_spans) ^ 0xC3C3C3C33C3C3C3Cull);
 }
-/* second lane of a term */
-PT_HD uint64_t pt_term_hi(uint64_t term) { return pt_mix64(term + 0x632BE59BD9B4E019ull); }
+/* second lane of a term (XOR-accumulated) */
+PT_HD uint64_t pt_term_hi(uint64_t term) { return (term << 23) | (term >> 41); }
 
 #endif

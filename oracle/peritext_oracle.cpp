@@ -940,7 +940,7 @@ static void replayOne(const pt_packed_ops* in, uint32_t li, const PackedOut& out
     uint32_t* text = out.text + out.text_off[li];
     pt_span* sp = out.spans + out.span_off[li];
     uint64_t d0 = 0, d1 = 0;
-    auto addTerm = [&](uint64_t t) { d0 += t; d1 += pt_term_hi(t); };
+    auto addTerm = [&](uint64_t t) { d0 += t; d1 ^= pt_term_hi(t); };
     for (uint32_t i = 0; i < R.n_visible; i++) { uint32_t tok; memcpy(&tok, list.text[i].data(), 4); text[i] = tok; addTerm(pt_term_text(i, tok)); }
     uint32_t start = 0;
     for (uint32_t j = 0; j < R.n_spans; j++) {

@@ -146,12 +146,12 @@ __device__ __forceinline__ uint32_t pack32(const uint8_t* b) {
     return nib(x.x) | (nib(x.y) << 4) | (nib(x.z) << 8) | (nib(x.w) << 12) | (nib(y.x) << 16) | (nib(y.y) << 20) | (nib(y.z) << 24) | (nib(y.w) << 28);
 }
 
-__device__ __forceinline__ void digest_add(unsigned long long& d0, unsigned long long& d1, uint64_t t) { d0 += t; d1 += pt_term_hi(t); }
+__device__ __forceinline__ void digest_add(unsigned long long& d0, unsigned long long& d1, uint64_t t) { d0 += t; d1 ^= pt_term_hi(t); }
 template <int BLOCK>
 __device__ __forceinline__ void digest_flush(BlockCtx<BLOCK>& c, unsigned long long d0, unsigned long long d1) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
-    if ((threadIdx.x & 31) == 0 && (d0 | d1)) { atomicAdd(&c.dig0, d0); atomicAdd(&c.dig1, d1); }
+    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 ^= __shfl_xor_sync(0xffffffffu, d1, o); }
+    if ((threadIdx.x & 31) == 0 && (d0 | d1)) { atomicAdd(&c.dig0, d0); atomicXor(&c.dig1, d1); }
 }
 
 // Euler-tour node: next (20 bits) | element weight (22 bits) | visible weight (22 bits)
@@ -182,7 +182,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     A.sm_cap = P.smem_arena_bytes; A.sm_used = 0;
     A.gm = P.slab + (unsigned long long)blockIdx.x * P.slab_bytes; A.gm_cap = P.slab_bytes; A.gm_used = 0; A.overflow = false;
 
-    if (tid == 0) { c.status = 0; c.misc[0] = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
+    if (tid == 0) { c.status = 0; c.misc[0] = 0; c.misc[2] = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
 
     auto keyOf = [&](uint32_t ctr, uint32_t actor) -> uint32_t { return (ctr - 1u) * R + actor; };
     auto badId = [&](uint32_t ctr, uint32_t actor) -> bool { return ctr - 1u >= C || actor >= R; };
@@ -284,14 +284,17 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     A.sm_used = mark_sm; A.gm_used = mark_gm;      // release Other / Del
     uint32_t N = 0;
     {
-        uint32_t cnt = 0;
+        uint32_t cnt = 0, ccnt = 0;
         for (uint32_t w = tid; w < NWr; w += BLOCK) cnt += __popc(InsBits[w]);
+        for (uint32_t k = tid; k < m; k += BLOCK) ccnt += (((uint32_t)mk[k].kind >> 1) & 3u) == PT_MARK_COMMENT ? 1u : 0u;   // sizes the comment tables
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); ccnt += __shfl_xor_sync(0xffffffffu, ccnt, o); }
         if (lane == 0 && cnt) atomicAdd(&c.misc[0], cnt);
+        if (lane == 0 && ccnt) atomicAdd(&c.misc[2], ccnt);
     }
     __syncthreads();
     N = c.misc[0];
+    const uint32_t McBound = c.misc[2];
     if (2ull * M + 4 >= (1ull << kNodeNxtBits) || N >= (1u << 22)) { if (tid == 0) c.status = PT_LOG_OVERFLOW; __syncthreads(); bail(); return 0; }
 
     auto runOf = [&](uint32_t i) -> uint32_t {     // run id of element record i
@@ -311,7 +314,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         if (m) {
             const unsigned long long NWp_ = (N + 32) / 32 + 1, KW_ = (KS + 31) / 32;
             const unsigned long long Sb = (2ull * m + 2 < (unsigned long long)N + 2 ? 2ull * m + 2 : (unsigned long long)N + 2) + 1;
-            const unsigned long long Mcb = m, Hb = 4 * Mcb + 8, VWb = (nvis + 31) / 32, nsp = nvis < 2ull * m + 1 ? nvis : 2ull * m + 1;
+            const unsigned long long Mcb = McBound, Hb = 4 * Mcb + 8, VWb = (nvis + 31) / 32, nsp = nvis < 2ull * m + 1 ? nvis : 2ull * m + 1;
             const unsigned long long Pm = base + 6 * al((m + 1) * I) + al(m + 1) + 2 * al((m + 1) * 4ull) + al((NWp_ + 1) * 4) + al((NWp_ + 1) * I);
             const unsigned long long pG2 = Pm + al((KW_ + 1) * 4) + al((KW_ + 1) * I);
             const unsigned long long Q = Pm + 2 * al((Sb + 1) * 4);
@@ -457,7 +460,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             span_out[0] = s;
             unsigned long long d0 = 0, d1 = 0;
             digest_add(d0, d1, pt_term_span(0, 0, 0, PT_ATTR_NONE));
-            atomicAdd(&c.dig0, d0); atomicAdd(&c.dig1, d1);
+            atomicAdd(&c.dig0, d0); atomicXor(&c.dig1, d1);
         }
         nspans = nvis ? 1u : 0u;
     } else {
@@ -813,7 +816,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         r.status = A.overflow ? PT_LOG_OVERFLOW : c.status;
         r.n_elems = N; r.n_visible = nvis; r.n_spans = nspans;
         uint64_t t = pt_term_counts(nvis, nspans);
-        r.digest[0] = c.dig0 + t; r.digest[1] = c.dig1 + pt_term_hi(t);
+        r.digest[0] = c.dig0 + t; r.digest[1] = c.dig1 ^ pt_term_hi(t);
         if (r.status) { r.n_elems = r.n_visible = r.n_spans = 0; r.digest[0] = r.digest[1] = 0; }
         *res = r;
     }

@@ -35,7 +35,7 @@ def term_text(i, tok): return _mix64(((i << 32) | tok) + 0x9E3779B97F4A7C15)
 def term_span(j, start, flags, link): return _mix64(_mix64(((j << 32) | start) ^ 0xA5A5A5A55A5A5A5A) + ((flags << 32) | link))
 def term_comment(j, k, cid): return _mix64(_mix64(((j << 32) | k) ^ 0x5BD1E9955BD1E995) + cid)
 def term_counts(nv, ns): return _mix64(((nv << 32) | ns) ^ 0xC3C3C3C33C3C3C3C)
-def term_hi(t): return _mix64(t + 0x632BE59BD9B4E019)
+def term_hi(t): return ((t << 23) | (t >> 41)) & MASK64
 
 
 EMPTY = -1
@@ -304,7 +304,7 @@ def merge_log(ins, mk, n_actors, max_ctr):
 
     def add(t):
         nonlocal d0, d1
-        d0 = (d0 + t) & MASK64; d1 = (d1 + term_hi(t)) & MASK64
+        d0 = (d0 + t) & MASK64; d1 = d1 ^ term_hi(t)
     for i, t in enumerate(tokens):
         add(term_text(i, t))
     for j, (st, fl, ln, cl) in enumerate(spans):
