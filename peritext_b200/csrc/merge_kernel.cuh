@@ -95,9 +95,25 @@ __device__ __forceinline__ void block_scan2(uint32_t va, uint32_t vb, BlockCtx<B
 }
 template <int BLOCK>
 __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, BlockCtx<BLOCK>& c, uint32_t& total) {
-    uint32_t ea, eb, tb;
-    block_scan2<BLOCK>(v, 0u, c, ea, eb, total, tb);
-    return ea;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+    if (BLOCK == 32) { total = __shfl_sync(0xffffffffu, x, 31); return x - v; }
+    if (lane == 31) c.warp_a[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (BLOCK / 32) ? c.warp_a[lane] : 0, s2 = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s2, o); if (lane >= (uint32_t)o) s2 += y; }
+        if (lane < (BLOCK / 32)) c.warp_a[lane] = s2 - w;
+        if (lane == 31) c.tot_a = s2;
+    }
+    __syncthreads();
+    const uint32_t res = c.warp_a[warp] + x - v;
+    total = c.tot_a;
+    __syncthreads();
+    return res;
 }
 
 extern __shared__ __align__(16) char ptk_smem[];   // dynamic shared memory = the arena's fast region
@@ -223,13 +239,9 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             else if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
             else if (kind == PT_KIND_INSERT) { isIns = true; T[keyOf(ctr, actor)] = (Idx)i; }
         }
-        // id and is-insert flag of record i-1: neighbour lane, one extra load for lane 0
-        uint32_t prev_ctr = __shfl_up_sync(0xffffffffu, ctr, 1);
-        uint32_t prev_pack = __shfl_up_sync(0xffffffffu, actor | (isIns ? 0x10000u : 0u), 1);
-        if (lane == 0) {
-            prev_ctr = 0; prev_pack = 0;
-            if (i > 0 && i < n) { const uint4 r = ld_rec(ins + i - 1); prev_ctr = r.x; prev_pack = (r.z & 0xFFFFu) | (((r.w >> 30) == PT_KIND_INSERT) ? 0x10000u : 0u); }
-        }
+        // id and is-insert flag of record i-1: every lane re-reads its left neighbour (same cache lines, L1 hit)
+        uint32_t prev_ctr = 0, prev_pack = 0;
+        if (isIns && i > 0) { const uint4 rp = ld_rec(ins + i - 1); prev_ctr = rp.x; prev_pack = (rp.z & 0xFFFFu) | (((rp.w >> 30) == PT_KIND_INSERT) ? 0x10000u : 0u); }
         bool cand = isIns && ref_ctr != 0 && ref_ctr == prev_ctr && (ref_actor | 0x10000u) == prev_pack;
         if (cand && keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); cand = false; }
         const uint32_t insW = __ballot_sync(0xffffffffu, isIns), candW = __ballot_sync(0xffffffffu, cand);
@@ -310,7 +322,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         auto al = [](unsigned long long b) -> unsigned long long { return (b + 15ull) & ~15ull; };
         const unsigned long long I = sizeof(Idx);
         const unsigned long long base = (unsigned long long)A.sm_used + 2 * al((M + 2) * 4ull);
-        unsigned long long peak = base + al((E + 1) * 8ull) + 5 * al((M + 1) * I) + al((M + 1) * 4ull) + al((M + 2) * I);
+        unsigned long long peak = base + al((E + 1) * 8ull) + al(((E + 7) / 8 + 3) * 8ull) + 5 * al((M + 1) * I) + al((M + 1) * 4ull) + al((M + 2) * I);
         if (m) {
             const unsigned long long NWp_ = (N + 32) / 32 + 1, KW_ = (KS + 31) / 32;
             const unsigned long long Sb = (2ull * m + 2 < (unsigned long long)N + 2 ? 2ull * m + 2 : (unsigned long long)N + 2) + 1;
@@ -333,6 +345,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     PT_ALLOC(VisBase, uint32_t, M + 2);   // vis(i) = VisBase[run] + visBefore(i)
     const uint32_t mark2_sm = A.sm_used; const unsigned long long mark2_gm = A.gm_used;   // run-tree temporaries, released after E
     PT_ALLOC(Node, unsigned long long, E + 1);   // E: Euler-tour nodes
+    PT_ALLOC(Sub, unsigned long long, (E + 7) / 8 + 3);   // splitter sublist summaries
     PT_ALLOC(RunHead, Idx, M + 1);
     PT_ALLOC(Prun, Idx, M + 1);
     PT_ALLOC(Key, uint32_t, M + 1);
@@ -345,20 +358,21 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     fill<uint32_t, BLOCK>(GrpCnt, M + 2, 0u);
     fill<uint32_t, BLOCK>(GrpCur, M + 2, 0u);
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += BLOCK) {        // one thread per record; run heads do the work
-        const uint32_t w = i >> 5, b = i & 31;
-        const uint32_t hw = HeadBits[w];
-        if (!((hw >> b) & 1u)) continue;
-        const uint32_t rid = (uint32_t)HeadPre[w] + __popc(hw & ((1u << b) - 1u));
+    for (uint32_t i = tid; i < n; i += BLOCK) {        // compact the run heads: RunHead[run] = record index
+        const uint32_t hw = HeadBits[i >> 5], b = i & 31;
+        if ((hw >> b) & 1u) RunHead[(uint32_t)HeadPre[i >> 5] + __popc(hw & ((1u << b) - 1u))] = (Idx)i;
+    }
+    __syncthreads();
+    for (uint32_t rid = tid; rid < M; rid += BLOCK) {  // one thread per run
+        const uint32_t i = RunHead[rid], w = i >> 5, b = i & 31;
         // run = insert records from i up to the next head or non-insert record
-        uint32_t stop = (hw | ~InsBits[w]) & ~(0xFFFFFFFFu >> (31 - b));
+        uint32_t stop = (HeadBits[w] | ~InsBits[w]) & ~(0xFFFFFFFFu >> (31 - b));
         uint32_t ww = w;
         while (!stop) { ww++; stop = HeadBits[ww] | ~InsBits[ww]; }     // pad word: InsBits == 0 -> stops
         const uint32_t end = ww * 32 + (__ffs(stop) - 1);
         const uint4 rec = ld_rec(ins + i);
         const uint32_t p = rec.y == 0 ? n : (uint32_t)T[keyOf(rec.y, rec.z >> 16)];
         const uint32_t q = p == n ? M : runOf(p);
-        RunHead[rid] = (Idx)i;
         Node[rid] = node_make(0, end - i, visBefore(end) - visBefore(i));   // weights now, successor in phase E
         Prun[rid] = (Idx)q;
         Key[rid] = keyOf(rec.x, rec.z & 0xFFFFu);
@@ -409,22 +423,49 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     }
     if (tid == 0) Node[END] = node_make(END, 0, 0);
     __syncthreads();
+    // Work-efficient ranking: every 8th node id (and the list head) is a SPLITTER.  (1) each splitter walks its sublist
+    // once, leaving in every visited node (owner splitter, weight prefix inside the sublist); (2) only the ~E/8 splitter
+    // summaries are ranked by pointer jumping; (3) suffix(x) = suffix(owner sublist) - prefix(x).
+    const uint32_t headNode = M;                              // enter(HEAD) starts the tour
+    const uint32_t nSp = (E + 7) / 8 + 1;                     // splitter ids: k < nSp-1 -> node 8k ; nSp-1 -> headNode (if not a multiple of 8)
+    const uint32_t SPEND = nSp;                               // terminator of the splitter list
+    auto spOf = [&](uint32_t x) -> uint32_t { return (x & 7u) == 0 ? (x >> 3) : nSp - 1; };
+    auto isSp = [&](uint32_t x) -> bool { return (x & 7u) == 0 || x == headNode; };
+    for (uint32_t k = tid; k < nSp; k += BLOCK) {
+        uint32_t cur = k + 1 < nSp ? 8 * k : headNode;
+        unsigned long long acc = 0;
+        bool valid = cur < E && (k + 1 < nSp || (headNode & 7u) != 0);
+        uint32_t nx = END;
+        if (valid) {
+            for (;;) {
+                const unsigned long long a = Node[cur];
+                nx = (uint32_t)(a & kNodeNxtMask);
+                Node[cur] = acc | k;                          // (owner, prefix before this node)
+                acc += a & ~kNodeNxtMask;
+                if (nx == END || isSp(nx)) break;
+                cur = nx;
+            }
+        }
+        Sub[k] = valid ? (acc | (nx == END ? SPEND : spOf(nx))) : (unsigned long long)SPEND;
+    }
+    if (tid == 0) Sub[SPEND] = SPEND;
+    __syncthreads();
     {
-        volatile unsigned long long* vn = Node;
-        for (uint32_t span = 1; span < E + 1; span <<= 1) {
-            for (uint32_t x = tid; x < E; x += BLOCK) {
-                const unsigned long long a = vn[x];
+        volatile unsigned long long* vs = Sub;
+        for (uint32_t span = 1; span < nSp + 1; span <<= 1) {
+            for (uint32_t x = tid; x < nSp; x += BLOCK) {
+                const unsigned long long a = vs[x];
                 const uint32_t nx = (uint32_t)(a & kNodeNxtMask);
-                if (nx == END) continue;
-                const unsigned long long b = vn[nx];
-                vn[x] = ((a & ~kNodeNxtMask) + (b & ~kNodeNxtMask)) | (b & kNodeNxtMask);
+                if (nx == SPEND) continue;
+                const unsigned long long b = vs[nx];
+                vs[x] = ((a & ~kNodeNxtMask) + (b & ~kNodeNxtMask)) | (b & kNodeNxtMask);
             }
             __syncthreads();
         }
     }
-    unsigned long long* nodeA = Node;   // weights of Node[r] = elements / visible elements from run r to the end of the sequence
     for (uint32_t r = tid; r < M; r += BLOCK) {
-        const unsigned long long a = nodeA[r];
+        const unsigned long long loc = Node[r];
+        const unsigned long long a = (Sub[(uint32_t)(loc & kNodeNxtMask)] & ~kNodeNxtMask) - (loc & ~kNodeNxtMask);   // elements / visible from run r to the end
         const uint32_t sufEl = (uint32_t)(a >> 20) & 0x3FFFFFu, sufVis = (uint32_t)(a >> 42);
         const uint32_t h = RunHead[r];
         PosBase[r] = (N - sufEl) - h;

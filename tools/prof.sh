@@ -1,0 +1,4 @@
+cd $GRAFT_REPO_ROOT
+# usage: prof.sh <tag> <config> <docs>
+ncu --set full --clock-control none --import-source on -k regex:merge_logs -s 3 -c 1 -o gpurun_out/prof_$1 python bench.py --config $2 --docs $3 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/prof_$1.log 2>&1
+tail -1 gpurun_out/prof_$1.log | cut -c1-160
