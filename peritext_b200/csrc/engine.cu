@@ -58,7 +58,7 @@ struct BinCfg { uint32_t max_recs; int block; uint32_t smem; int ctas_per_sm; };
 BinCfg kBins[kNumBins] = {
     {1536u, 128, 31u * 1024u, 7},
     {4096u, 256, 74u * 1024u, 3},
-    {6144u, 512, 112u * 1024u, 2},
+    {12288u, 512, 112u * 1024u, 2},
     {0xFFFFFFFFu, 1024, 226u * 1024u, 1},
 };
 
@@ -73,7 +73,7 @@ size_t arena_worst_bytes(uint64_t n, uint64_t m, uint64_t KS) {
     const uint64_t NWr = (n + 31) / 32 + 1;
     A(KS, I); A(NWr, 4); A(NWr, 4); A(NWr, 4); A(NWr, I); A(NWr, I);               // T InsBits HeadBits VisBits HeadPre VisPre
     A(NWr * 32 + 32, 1); A(NWr * 32 + 32, 1);                                      // Other Del
-    A(2 * n + 3, 8);                                                               // Node
+    A(2 * n + 3, 8); A((2 * n + 9) / 8 + 3, 8);                                    // Node Sub
     A(n + 1, I); A(n + 2, 4); A(n + 2, 4); A(n + 1, I); A(n + 1, 4); A(n + 2, I);  // RunHead PosBase VisBase Prun Key GrpOff
     A(n + 1, I); A(n + 1, I); A(n + 1, I);                                         // Unsorted Sorted SPos
     if (m) {
@@ -107,8 +107,9 @@ struct pt_batch {
     std::vector<uint32_t> h_order;
     uint32_t bin_first[kNumBins + 1] = {0};
     size_t bin_slab[kNumBins] = {0};
+    size_t retry_slab = 0;
     // device
-    DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_pool_used, d_slab, d_stats;
+    DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_pool_used, d_slab, d_stats, d_retry;
     const pt_insdel_rec* dp_insdel = nullptr;
     const pt_mark_rec* dp_marks = nullptr;
     // pinned host
@@ -185,7 +186,7 @@ int alloc_and_upload_plan(pt_batch* b) {
     const size_t n = b->n_logs;
     if ((rc = b->d_desc.reserve(std::max<size_t>(1, n) * sizeof(pt_log_desc)))) return rc;
     if ((rc = b->d_order.reserve(std::max<size_t>(1, n) * 4))) return rc;
-    if ((rc = b->d_counters.reserve(kNumBins * 4))) return rc;
+    if ((rc = b->d_counters.reserve((kNumBins + 4) * 4))) return rc;
     if ((rc = b->d_results.reserve(std::max<size_t>(1, n) * sizeof(pt_log_result)))) return rc;
     if ((rc = b->d_text_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
     if ((rc = b->d_span_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
@@ -194,13 +195,15 @@ int alloc_and_upload_plan(pt_batch* b) {
     if ((rc = b->d_pool.reserve(std::max<uint64_t>(1, b->pool_cap) * 4))) return rc;
     if ((rc = b->d_pool_used.reserve(8))) return rc;
     if ((rc = b->d_stats.reserve(64))) return rc;
-    size_t slab_total = 0;
-    for (int k = 0; k < kNumBins; k++) {
-        uint32_t cnt = b->bin_first[k + 1] - b->bin_first[k];
-        if (!cnt) continue;
-        size_t grid = std::min<size_t>(cnt, (size_t)b->num_sms * kBins[k].ctas_per_sm);
-        slab_total = std::max(slab_total, grid * b->bin_slab[k]);
+    if ((rc = b->d_retry.reserve(std::max<size_t>(1, n) * 4 + 16))) return rc;
+    size_t slab_total = 0, slab_max = 0;
+    for (int k = 0; k < kNumBins; k++) slab_max = std::max(slab_max, b->bin_slab[k]);
+    {   // only the last bin and the retry launch can spill
+        uint32_t cnt = b->bin_first[kNumBins] - b->bin_first[kNumBins - 1];
+        size_t grid = std::min<size_t>(cnt, (size_t)b->num_sms * kBins[kNumBins - 1].ctas_per_sm);
+        slab_total = std::max(grid * b->bin_slab[kNumBins - 1], (size_t)b->num_sms * kBins[kNumBins - 1].ctas_per_sm * slab_max);
     }
+    b->retry_slab = slab_max;
     if ((rc = b->d_slab.reserve(std::max<size_t>(slab_total, 16)))) return rc;
     // stage the small host-derived arrays through pinned memory
     size_t stage = n * (sizeof(pt_log_desc) + 4 + 8 + 8) + 64;
@@ -220,29 +223,38 @@ int alloc_and_upload_plan(pt_batch* b) {
 }
 
 template <int BLOCK>
-int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P) {
-    uint32_t cnt = b->bin_first[k + 1] - b->bin_first[k];
-    uint32_t grid = (uint32_t)std::min<size_t>(cnt, (size_t)b->num_sms * kBins[k].ctas_per_sm);
-    P.order = (const uint32_t*)b->d_order.p + b->bin_first[k];
-    P.n_work = cnt;
-    P.work_counter = (uint32_t*)b->d_counters.p + k;
-    P.slab_bytes = b->bin_slab[k];
-    P.smem_arena_bytes = kBins[k].smem;
-    PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_kernel<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBins[k].smem));
-    ptk::merge_logs_kernel<BLOCK><<<grid, BLOCK, kBins[k].smem, b->stream>>>(P);
+int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P, bool retry) {
+    const BinCfg& cfg = kBins[retry ? kNumBins - 1 : k];
+    uint32_t cnt = retry ? b->n_logs : b->bin_first[k + 1] - b->bin_first[k];
+    uint32_t grid = (uint32_t)std::min<size_t>(cnt, (size_t)b->num_sms * cfg.ctas_per_sm);
+    uint32_t* counters = (uint32_t*)b->d_counters.p;
+    if (retry) {
+        P.order = (const uint32_t*)b->d_retry.p; P.n_work = 0; P.n_work_dev = counters + kNumBins + 1;
+        P.work_counter = counters + kNumBins; P.slab_bytes = b->retry_slab;
+        P.retry_list = nullptr; P.retry_count = nullptr;
+    } else {
+        P.order = (const uint32_t*)b->d_order.p + b->bin_first[k]; P.n_work = cnt; P.n_work_dev = nullptr;
+        P.work_counter = counters + k; P.slab_bytes = b->bin_slab[k];
+        const bool last = k == kNumBins - 1;
+        P.retry_list = last ? nullptr : (uint32_t*)b->d_retry.p;
+        P.retry_count = last ? nullptr : counters + kNumBins + 1;
+    }
+    P.smem_arena_bytes = cfg.smem;
+    PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_kernel<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    ptk::merge_logs_kernel<BLOCK><<<grid, BLOCK, cfg.smem, b->stream>>>(P);
     PT_CUDA(cudaGetLastError());
     b->launches++;
     return PT_OK;
 }
-int launch_bin(pt_batch* b, int k, const ptk::BatchParams& P) {
-    if (b->bin_first[k + 1] == b->bin_first[k]) return PT_OK;
-    switch (kBins[k].block) {
-        case 32: return launch_bin_t<32>(b, k, P);
-        case 64: return launch_bin_t<64>(b, k, P);
-        case 128: return launch_bin_t<128>(b, k, P);
-        case 256: return launch_bin_t<256>(b, k, P);
-        case 512: return launch_bin_t<512>(b, k, P);
-        default: return launch_bin_t<1024>(b, k, P);
+int launch_bin(pt_batch* b, int k, const ptk::BatchParams& P, bool retry) {
+    if (!retry && b->bin_first[k + 1] == b->bin_first[k]) return PT_OK;
+    switch (kBins[retry ? kNumBins - 1 : k].block) {
+        case 32: return launch_bin_t<32>(b, k, P, retry);
+        case 64: return launch_bin_t<64>(b, k, P, retry);
+        case 128: return launch_bin_t<128>(b, k, P, retry);
+        case 256: return launch_bin_t<256>(b, k, P, retry);
+        case 512: return launch_bin_t<512>(b, k, P, retry);
+        default: return launch_bin_t<1024>(b, k, P, retry);
     }
 }
 
@@ -306,7 +318,7 @@ int pt_batch_merge(pt_batch* b) {
     if (!b->have_batch) { g_last_error = "pt_batch_merge before pt_batch_upload"; return PT_ERR_STATE; }
     PT_CUDA(cudaSetDevice(b->device));
     PT_CUDA(cudaEventRecord(b->ev0, b->stream));
-    PT_CUDA(cudaMemsetAsync(b->d_counters.p, 0, kNumBins * 4, b->stream));
+    PT_CUDA(cudaMemsetAsync(b->d_counters.p, 0, (kNumBins + 4) * 4, b->stream));
     PT_CUDA(cudaMemsetAsync(b->d_pool_used.p, 0, 8, b->stream));
     PT_CUDA(cudaMemsetAsync(b->d_stats.p, 0, 64, b->stream));
     ptk::BatchParams P{};
@@ -320,7 +332,9 @@ int pt_batch_merge(pt_batch* b) {
     P.stats = (unsigned long long*)b->d_stats.p;
     int rc;
     // largest logs first: the long-running CTAs start earliest
-    for (int k = kNumBins - 1; k >= 0; k--) if ((rc = launch_bin(b, k, P))) return rc;
+    for (int k = kNumBins - 1; k >= 0; k--) if ((rc = launch_bin(b, k, P, false))) return rc;
+    // logs whose working set did not fit their bin's shared memory, re-run with the largest budget (count lives on the device)
+    if (b->bin_first[kNumBins - 1] > 0 && (rc = launch_bin(b, 0, P, true))) return rc;
     PT_CUDA(cudaEventRecord(b->ev1, b->stream));
     b->merged = true;
     return PT_OK;
@@ -410,7 +424,7 @@ void pt_batch_destroy(pt_batch* b) {
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
-                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_pool_used, &b->d_slab, &b->d_stats}) d->release();
+                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_pool_used, &b->d_slab, &b->d_stats, &b->d_retry}) d->release();
     for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc}) h->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);

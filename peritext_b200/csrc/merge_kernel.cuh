@@ -44,7 +44,10 @@ struct BatchParams {
     char* slab;                           // spill: slab_bytes per CTA
     unsigned long long slab_bytes;
     uint32_t smem_arena_bytes;            // dynamic shared memory given to the arena
-    unsigned long long* stats;            // [0] logs finished on the shared-only path, [1] restarts on the spill path
+    unsigned long long* stats;            // [0] logs finished on the shared-only path, [1] on the spill path, [2] deferred
+    uint32_t* retry_list;                 // non-null: logs that do not fit this bin's shared memory are deferred here
+    uint32_t* retry_count;
+    const uint32_t* n_work_dev;           // non-null: number of work items is read from device memory (retry launch)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -870,16 +873,17 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : BLOCK == 128 ? 7 : BLOCK == 64 ? 8 : BLOCK == 32 ? 8 : 1)) merge_logs_kernel(const BatchParams P) {
     __shared__ BlockCtx<BLOCK> ctx;
+    const uint32_t n_work = P.n_work_dev ? *P.n_work_dev : P.n_work;
     if (threadIdx.x == 0) ctx.work_next = atomicAdd(P.work_counter, 1u);
     __syncthreads();
     for (;;) {
         const uint32_t w = ctx.work_next;
         __syncthreads();
-        if (w >= P.n_work) break;
+        if (w >= n_work) break;
         if (threadIdx.x == 0) ctx.work_next = atomicAdd(P.work_counter, 1u);
         __syncthreads();
         const uint32_t wn = ctx.work_next;
-        if (wn < P.n_work) {
+        if (wn < n_work) {
             const pt_log_desc& Ln = P.desc[P.order[wn]];
             const char* p0 = reinterpret_cast<const char*>(P.insdel + Ln.insdel_off);
             const uint32_t lines = (uint32_t)(((unsigned long long)Ln.n_insdel * sizeof(pt_insdel_rec) + 127) >> 7);
@@ -890,8 +894,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : 
         const bool small = L.n_insdel < 32000u && L.n_mark < 32000u;
         // optimistic: everything in shared memory (LDS/STS); restart with the spill-capable variant if it does not fit
         int spill;
-        if (small) { spill = merge_one_log<uint16_t, BLOCK, true>(P, li, ctx); if (spill) { __syncthreads(); merge_one_log<uint16_t, BLOCK, false>(P, li, ctx); } }
-        else { spill = merge_one_log<uint32_t, BLOCK, true>(P, li, ctx); if (spill) { __syncthreads(); merge_one_log<uint32_t, BLOCK, false>(P, li, ctx); } }
+        if (small) spill = merge_one_log<uint16_t, BLOCK, true>(P, li, ctx); else spill = merge_one_log<uint32_t, BLOCK, true>(P, li, ctx);
+        if (spill) {
+            __syncthreads();
+            if (P.retry_list) {            // defer to the launch with the largest shared-memory budget
+                if (threadIdx.x == 0) { P.retry_list[atomicAdd(P.retry_count, 1u)] = li; atomicAdd(&P.stats[2], 1ull); }
+                continue;
+            }
+            if (small) merge_one_log<uint16_t, BLOCK, false>(P, li, ctx); else merge_one_log<uint32_t, BLOCK, false>(P, li, ctx);
+        }
         if (threadIdx.x == 0) atomicAdd(&P.stats[spill ? 1 : 0], 1ull);
     }
 }

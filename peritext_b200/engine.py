@@ -122,7 +122,7 @@ class BatchEngine:
     def stats(self) -> dict:
         out = (ctypes.c_uint64 * 4)()
         _check(self._L.pt_batch_stats(self._h, ctypes.byref(out)), "pt_batch_stats")
-        return {"logs_shared_only": int(out[0]), "logs_spill_restart": int(out[1])}
+        return {"logs_shared_only": int(out[0]), "logs_spill_path": int(out[1]), "logs_deferred_to_big_bin": int(out[2])}
 
     def device_results_ptr(self) -> int:
         p = ctypes.c_void_p(); n = ctypes.c_uint32()
