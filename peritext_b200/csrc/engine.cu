@@ -186,7 +186,7 @@ int alloc_and_upload_plan(pt_batch* b) {
     const size_t n = b->n_logs;
     if ((rc = b->d_desc.reserve(std::max<size_t>(1, n) * sizeof(pt_log_desc)))) return rc;
     if ((rc = b->d_order.reserve(std::max<size_t>(1, n) * 4))) return rc;
-    if ((rc = b->d_counters.reserve((kNumBins + 4) * 4))) return rc;
+    if ((rc = b->d_counters.reserve((3 * kNumBins) * 4))) return rc;
     if ((rc = b->d_results.reserve(std::max<size_t>(1, n) * sizeof(pt_log_result)))) return rc;
     if ((rc = b->d_text_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
     if ((rc = b->d_span_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
@@ -195,14 +195,10 @@ int alloc_and_upload_plan(pt_batch* b) {
     if ((rc = b->d_pool.reserve(std::max<uint64_t>(1, b->pool_cap) * 4))) return rc;
     if ((rc = b->d_pool_used.reserve(8))) return rc;
     if ((rc = b->d_stats.reserve(64))) return rc;
-    if ((rc = b->d_retry.reserve(std::max<size_t>(1, n) * 4 + 16))) return rc;
+    if ((rc = b->d_retry.reserve(std::max<size_t>(1, n) * 4 * kNumBins + 16))) return rc;
     size_t slab_total = 0, slab_max = 0;
     for (int k = 0; k < kNumBins; k++) slab_max = std::max(slab_max, b->bin_slab[k]);
-    {   // only the last bin and the retry launch can spill
-        uint32_t cnt = b->bin_first[kNumBins] - b->bin_first[kNumBins - 1];
-        size_t grid = std::min<size_t>(cnt, (size_t)b->num_sms * kBins[kNumBins - 1].ctas_per_sm);
-        slab_total = std::max(grid * b->bin_slab[kNumBins - 1], (size_t)b->num_sms * kBins[kNumBins - 1].ctas_per_sm * slab_max);
-    }
+    slab_total = (size_t)b->num_sms * kBins[kNumBins - 1].ctas_per_sm * slab_max;   // only the last bin can spill
     b->retry_slab = slab_max;
     if ((rc = b->d_slab.reserve(std::max<size_t>(slab_total, 16)))) return rc;
     // stage the small host-derived arrays through pinned memory
@@ -222,23 +218,26 @@ int alloc_and_upload_plan(pt_batch* b) {
     return PT_OK;
 }
 
+// counters: [0,kNumBins) work-queue heads of the bins' own lists, [kNumBins, 2k) heads of the retry launches,
+// [2k, 3k) number of logs deferred INTO bin k (list k of d_retry)
 template <int BLOCK>
 int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P, bool retry) {
-    const BinCfg& cfg = kBins[retry ? kNumBins - 1 : k];
+    const BinCfg& cfg = kBins[k];
     uint32_t cnt = retry ? b->n_logs : b->bin_first[k + 1] - b->bin_first[k];
     uint32_t grid = (uint32_t)std::min<size_t>(cnt, (size_t)b->num_sms * cfg.ctas_per_sm);
     uint32_t* counters = (uint32_t*)b->d_counters.p;
+    uint32_t* lists = (uint32_t*)b->d_retry.p;
     if (retry) {
-        P.order = (const uint32_t*)b->d_retry.p; P.n_work = 0; P.n_work_dev = counters + kNumBins + 1;
-        P.work_counter = counters + kNumBins; P.slab_bytes = b->retry_slab;
-        P.retry_list = nullptr; P.retry_count = nullptr;
+        P.order = lists + (size_t)k * b->n_logs; P.n_work = 0; P.n_work_dev = counters + 2 * kNumBins + k;
+        P.work_counter = counters + kNumBins + k;
     } else {
         P.order = (const uint32_t*)b->d_order.p + b->bin_first[k]; P.n_work = cnt; P.n_work_dev = nullptr;
-        P.work_counter = counters + k; P.slab_bytes = b->bin_slab[k];
-        const bool last = k == kNumBins - 1;
-        P.retry_list = last ? nullptr : (uint32_t*)b->d_retry.p;
-        P.retry_count = last ? nullptr : counters + kNumBins + 1;
+        P.work_counter = counters + k;
     }
+    const bool last = k == kNumBins - 1;
+    P.slab_bytes = last ? b->retry_slab : 0;
+    P.retry_list = last ? nullptr : lists + (size_t)(k + 1) * b->n_logs;
+    P.retry_count = last ? nullptr : counters + 2 * kNumBins + (k + 1);
     P.smem_arena_bytes = cfg.smem;
     PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_kernel<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     ptk::merge_logs_kernel<BLOCK><<<grid, BLOCK, cfg.smem, b->stream>>>(P);
@@ -248,7 +247,7 @@ int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P, bool retry) {
 }
 int launch_bin(pt_batch* b, int k, const ptk::BatchParams& P, bool retry) {
     if (!retry && b->bin_first[k + 1] == b->bin_first[k]) return PT_OK;
-    switch (kBins[retry ? kNumBins - 1 : k].block) {
+    switch (kBins[k].block) {
         case 32: return launch_bin_t<32>(b, k, P, retry);
         case 64: return launch_bin_t<64>(b, k, P, retry);
         case 128: return launch_bin_t<128>(b, k, P, retry);
@@ -318,7 +317,7 @@ int pt_batch_merge(pt_batch* b) {
     if (!b->have_batch) { g_last_error = "pt_batch_merge before pt_batch_upload"; return PT_ERR_STATE; }
     PT_CUDA(cudaSetDevice(b->device));
     PT_CUDA(cudaEventRecord(b->ev0, b->stream));
-    PT_CUDA(cudaMemsetAsync(b->d_counters.p, 0, (kNumBins + 4) * 4, b->stream));
+    PT_CUDA(cudaMemsetAsync(b->d_counters.p, 0, (3 * kNumBins) * 4, b->stream));
     PT_CUDA(cudaMemsetAsync(b->d_pool_used.p, 0, 8, b->stream));
     PT_CUDA(cudaMemsetAsync(b->d_stats.p, 0, 64, b->stream));
     ptk::BatchParams P{};
@@ -332,9 +331,14 @@ int pt_batch_merge(pt_batch* b) {
     P.stats = (unsigned long long*)b->d_stats.p;
     int rc;
     // largest logs first: the long-running CTAs start earliest
-    for (int k = kNumBins - 1; k >= 0; k--) if ((rc = launch_bin(b, k, P, false))) return rc;
-    // logs whose working set did not fit their bin's shared memory, re-run with the largest budget (count lives on the device)
-    if (b->bin_first[kNumBins - 1] > 0 && (rc = launch_bin(b, 0, P, true))) return rc;
+    // ascending bins; a log whose working set does not fit bin k's shared memory is deferred (on the device) to bin k+1;
+    // only the last bin can spill to the global slab
+    bool lower = false;
+    for (int k = 0; k < kNumBins; k++) {
+        if ((rc = launch_bin(b, k, P, false))) return rc;
+        if (k > 0 && lower && (rc = launch_bin(b, k, P, true))) return rc;
+        lower = lower || b->bin_first[k + 1] > b->bin_first[k];
+    }
     PT_CUDA(cudaEventRecord(b->ev1, b->stream));
     b->merged = true;
     return PT_OK;

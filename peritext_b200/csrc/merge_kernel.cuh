@@ -897,7 +897,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : 
         if (small) spill = merge_one_log<uint16_t, BLOCK, true>(P, li, ctx); else spill = merge_one_log<uint32_t, BLOCK, true>(P, li, ctx);
         if (spill) {
             __syncthreads();
-            if (P.retry_list) {            // defer to the launch with the largest shared-memory budget
+            if (P.retry_list) {            // defer to the next bin (larger shared-memory budget)
                 if (threadIdx.x == 0) { P.retry_list[atomicAdd(P.retry_count, 1u)] = li; atomicAdd(&P.stats[2], 1ull); }
                 continue;
             }
