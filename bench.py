@@ -72,6 +72,19 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(config, n_docs):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json),
+    valid for the same config and docs-per-GPU; None otherwise."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        e = json.load(open(p)).get(config)
+        if e and int(e.get("docs_per_gpu", -1)) == int(n_docs):
+            return float(e["dram_bytes_per_launch"]), e.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 def cpu_baseline(batch, budget_s=20.0):
     """Times the oracle (sequential reference algorithm) on a bounded sample of the same workload, all host cores."""
     from oracle.packed import replay_packed
@@ -231,7 +244,6 @@ def main():
     lone = []
     for _ in range(min(5, args.steps)):
         eng.merge(); eng.sync(); lone.append(eng.last_merge_ms)
-    stop_evt.set(); th.join(timeout=2)
 
     results = eng.results()
     ok = bool((results["status"] == 0).all())
@@ -261,6 +273,8 @@ def main():
         d2h = merged.results.nbytes + merged.text.nbytes + merged.spans.nbytes + merged.comment_pool.nbytes
         e2e = {"ms": e_ms, "h2d": in_bytes, "d2h": int(d2h)}
 
+    stop_evt.set(); th.join(timeout=2)
+
     # reduce over ranks: time = max, work = sum
     t_ms = elapsed_ms
     if world > 1:
@@ -278,6 +292,7 @@ def main():
         lone_ms = sorted(lone)[len(lone) // 2]
         peak, peak_src = hbm_peak()
         achieved = alg_bytes / (lone_ms / 1e3) / 1e9
+        traffic, traffic_src = ncu_traffic(args.config, n_docs)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
@@ -291,7 +306,7 @@ def main():
                        "docs_per_sec": (n_logs * world) / (ms_per_step / 1e3), "kernel_paths": eng.stats()},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "ptk::merge_logs_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": lone_ms},
             "clocks": clocks_summary(samples),
         }
