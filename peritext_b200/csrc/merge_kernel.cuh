@@ -826,12 +826,16 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         __syncthreads();
         if (c.status) { bail(); return 0; }
         uint32_t* pool = P.comment_pool + c.pool_base;
+        // build and sort the lists in shared memory when they fit (latency of the per-span sort), else in the pool itself
+        const uint32_t slBytes = (totalC * 4u + 15u) & ~15u;
+        const bool staged = totalC > 0 && A.sm_used + slBytes <= A.sm_cap;
+        uint32_t* SL = staged ? reinterpret_cast<uint32_t*>(ptk_smem + A.sm_used) : pool;
         for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
             uint32_t va = PcA[e], vb = PcB[e];
             if (va >= vb) continue;
             const uint32_t id = CId[e >> 1];
             for (uint32_t j = headRank(va), j1 = headRank(vb); j < j1; j++)
-                pool[SpanCO[j] + atomicAdd(&SpanCur[j], 1u)] = id;
+                SL[SpanCO[j] + atomicAdd(&SpanCur[j], 1u)] = id;
         }
         __syncthreads();
         {
@@ -839,7 +843,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             for (uint32_t j = tid; j < nspans; j += BLOCK) {                // one thread per span
                 const uint32_t v = SpanStart[j], s2 = VisSeg[v];
                 const uint32_t cnt = SpanCC[j];
-                uint32_t* lst = pool + SpanCO[j];
+                uint32_t* lst = SL + SpanCO[j];
                 for (uint32_t x = 1; x < cnt; x++) {                        // insertion sort: ascending comment id
                     uint32_t key = lst[x]; uint32_t y = x;
                     while (y > 0 && lst[y - 1] > key) { lst[y] = lst[y - 1]; y--; }
@@ -850,6 +854,10 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
                 span_out[j] = sp;
                 for (uint32_t x = 0; x < cnt; x++) digest_add(d0, d1, pt_term_comment(j, x, lst[x]));
                 digest_add(d0, d1, pt_term_span(j, sp.start, sp.flags, sp.link_attr));
+            }
+            if (staged) {
+                __syncthreads();
+                for (uint32_t x = tid; x < totalC; x += BLOCK) pool[x] = SL[x];   // coalesced copy to the comment pool
             }
             digest_flush<BLOCK>(c, d0, d1);
         }
