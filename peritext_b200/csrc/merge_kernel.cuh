@@ -230,46 +230,55 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
 
     // ---- A: id table + insert / chain-continuation bitmaps (first and only HBM read of the records) ------------
     // cand(i): record i is an insert whose reference element is the insert at record i-1 (a typing chain link)
-    for (uint32_t base = 0; base < n; base += BLOCK) {
-        const uint32_t i = base + tid;
-        uint32_t ctr = 0, actor = 0, ref_ctr = 0, ref_actor = 0;
-        bool isIns = false;
-        if (i < n) {
-            const uint4 r = ld_rec(ins + i);
-            ctr = r.x; actor = r.z & 0xFFFFu; ref_ctr = r.y; ref_actor = r.z >> 16;
-            const uint32_t kind = r.w >> 30;
-            if (kind > 1u) fail(PT_LOG_BAD_KIND);
-            else if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
-            else if (kind == PT_KIND_INSERT) { isIns = true; T[keyOf(ctr, actor)] = (Idx)i; }
+    {
+        const uint4 zero4 = make_uint4(0, 0, 0, 0xC0000000u);     // kind 3: neither insert nor delete
+        auto stepA = [&](uint32_t i, const uint4 r, const uint4 rp) {
+            const uint32_t ctr = r.x, actor = r.z & 0xFFFFu, ref_ctr = r.y, ref_actor = r.z >> 16, kind = r.w >> 30;
+            bool isIns = false;
+            if (i < n) {
+                if (kind > 1u) fail(PT_LOG_BAD_KIND);
+                else if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
+                else if (kind == PT_KIND_INSERT) { isIns = true; T[keyOf(ctr, actor)] = (Idx)i; }
+            }
+            // reference element == the insert at record i-1 ?
+            bool cand = isIns && ref_ctr != 0 && ref_ctr == rp.x && ref_actor == (rp.z & 0xFFFFu) && (rp.w >> 30) == PT_KIND_INSERT;
+            if (cand && keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); cand = false; }
+            const uint32_t insW = __ballot_sync(0xffffffffu, isIns), candW = __ballot_sync(0xffffffffu, cand);
+            if (lane == 0 && i < n) { InsBits[i >> 5] = insW; HeadBits[i >> 5] = candW; }
+        };
+        for (uint32_t base = 0; base < n; base += 2 * BLOCK) {     // two records per thread per trip: 4 loads in flight
+            const uint32_t i0 = base + tid, i1 = i0 + BLOCK;
+            const uint4 r0 = i0 < n ? ld_rec(ins + i0) : zero4, r1 = i1 < n ? ld_rec(ins + i1) : zero4;
+            // the left neighbours (same cache lines, L1 hits)
+            const uint4 p0 = (i0 > 0 && i0 < n) ? ld_rec(ins + i0 - 1) : zero4, p1 = i1 < n ? ld_rec(ins + i1 - 1) : zero4;
+            stepA(i0, r0, p0);
+            stepA(i1, r1, p1);
         }
-        // id and is-insert flag of record i-1: every lane re-reads its left neighbour (same cache lines, L1 hit)
-        uint32_t prev_ctr = 0, prev_pack = 0;
-        if (isIns && i > 0) { const uint4 rp = ld_rec(ins + i - 1); prev_ctr = rp.x; prev_pack = (rp.z & 0xFFFFu) | (((rp.w >> 30) == PT_KIND_INSERT) ? 0x10000u : 0u); }
-        bool cand = isIns && ref_ctr != 0 && ref_ctr == prev_ctr && (ref_actor | 0x10000u) == prev_pack;
-        if (cand && keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); cand = false; }
-        const uint32_t insW = __ballot_sync(0xffffffffu, isIns), candW = __ballot_sync(0xffffffffu, cand);
-        if (lane == 0 && i < n) { InsBits[i >> 5] = insW; HeadBits[i >> 5] = candW; }
     }
     __syncthreads();
     if (c.status) { bail(); return 0; }
 
-    // ---- B: parents of chain heads (-> "has another child" flags), deletes (-> tombstones) ------------------------
-    for (uint32_t base = 0; base < n; base += BLOCK) {
-        const uint32_t i = base + tid;
-        if (i >= n) continue;
-        if ((HeadBits[i >> 5] >> (i & 31)) & 1u) continue;            // chain link: parent is record i-1, no lookup
-        uint4 r = ld_rec(ins + i);
-        const uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16, kind = r.w >> 30;
-        if (kind == PT_KIND_INSERT) {
-            if (ref_ctr == 0) continue;                                 // child of HEAD
-            Idx j = badId(ref_ctr, ref_actor) ? NONE : T[keyOf(ref_ctr, ref_actor)];
-            if (j == NONE) { fail(PT_LOG_ELEM_NOT_FOUND); continue; }
-            if (keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); continue; }
-            Other[j] = 1;
-        } else {
-            Idx j = (ref_ctr == 0 || badId(ref_ctr, ref_actor)) ? NONE : T[keyOf(ref_ctr, ref_actor)];
-            if (j == NONE) { fail(PT_LOG_ELEM_NOT_FOUND); continue; }
-            Del[j] = 1;                                                 // OR over deletes: idempotent (micromerge.ts:689)
+    // ---- B: parents of chain heads (-> "has another child" flags), deletes (-> tombstones): one code path for both ----
+    {
+        auto stepB = [&](uint32_t i, bool live, const uint4 r) {
+            if (!live) return;
+            const uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16;
+            const bool isIns = (r.w >> 30) == PT_KIND_INSERT;
+            if (ref_ctr == 0) { if (!isIns) fail(PT_LOG_ELEM_NOT_FOUND); return; }        // insert: child of HEAD
+            const Idx j = badId(ref_ctr, ref_actor) ? NONE : T[keyOf(ref_ctr, ref_actor)];
+            if (j == NONE) { fail(PT_LOG_ELEM_NOT_FOUND); return; }
+            if (isIns && keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); return; }
+            (isIns ? Other : Del)[j] = 1;        // deletes: OR, idempotent (micromerge.ts:689)
+        };
+        for (uint32_t base = 0; base < n; base += 2 * BLOCK) {
+            const uint32_t i0 = base + tid, i1 = i0 + BLOCK;
+            // chain links need no lookup: their parent is record i-1
+            const bool l0 = i0 < n && !((HeadBits[i0 >> 5] >> (i0 & 31)) & 1u), l1 = i1 < n && !((HeadBits[i1 >> 5] >> (i1 & 31)) & 1u);
+            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+            if (l0) r0 = ld_rec(ins + i0);
+            if (l1) r1 = ld_rec(ins + i1);
+            stepB(i0, l0, r0);
+            stepB(i1, l1, r1);
         }
     }
     __syncthreads();
@@ -483,15 +492,23 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     // ---- F: text out (visible index = prefix count of non-deleted elements, micromerge.ts:747-750) + duplicate-id check --
     {
         unsigned long long d0 = 0, d1 = 0;
-        for (uint32_t i = tid; i < n; i += BLOCK) {
-            if (!((InsBits[i >> 5] >> (i & 31)) & 1u)) continue;
-            const uint4 r = ld_rec(ins + i);
+        auto stepF = [&](uint32_t i, bool live, const uint4 r) {
+            if (!live) return;
             if ((uint32_t)T[keyOf(r.x, r.z & 0xFFFFu)] != i) fail(PT_LOG_BAD_OPID);     // two inserts with one opId
-            if (!isVis(i)) continue;
+            if (!isVis(i)) return;
             const uint32_t tok = PT_PAYLOAD_TOKEN(r.w);
             const uint32_t vr = visOf(i);
             text_out[vr] = tok;
             digest_add(d0, d1, pt_term_text(vr, tok));
+        };
+        for (uint32_t base = 0; base < n; base += 2 * BLOCK) {
+            const uint32_t i0 = base + tid, i1 = i0 + BLOCK;
+            const bool l0 = i0 < n && ((InsBits[i0 >> 5] >> (i0 & 31)) & 1u), l1 = i1 < n && ((InsBits[i1 >> 5] >> (i1 & 31)) & 1u);
+            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+            if (l0) r0 = ld_rec(ins + i0);
+            if (l1) r1 = ld_rec(ins + i1);
+            stepF(i0, l0, r0);
+            stepF(i1, l1, r1);
         }
         digest_flush<BLOCK>(c, d0, d1);
     }
