@@ -161,9 +161,16 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
         so += std::min<uint64_t>(L.n_insdel, 2ull * L.n_mark + 1);
         ncomment_bound += L.n_mark;
         uint64_t recs = (uint64_t)L.n_insdel + L.n_mark;
-        int bin = 0; while (recs > kBins[bin].max_recs) bin++;
-        bins[bin].push_back(i);
         uint64_t KS = (uint64_t)L.max_ctr * (L.n_actors ? L.n_actors : 1);
+        int bin = 0; while (recs > kBins[bin].max_recs) bin++;
+        // typical shared-memory need (runs ~ n/6, segments ~ min(2m, n/2)); a wrong guess only costs a device-side deferral
+        {
+            const uint64_t I = (L.n_insdel < 32000 && L.n_mark < 32000) ? 2 : 4, n_ = L.n_insdel, m_ = L.n_mark;
+            const uint64_t seg = std::min<uint64_t>(2 * m_ + 2, n_ / 2 + 2);
+            const uint64_t typical = KS * I + 6 * n_ + (m_ ? m_ * (6 * I + 9) + 32 * seg + 4096 : 0);
+            while (bin < kNumBins - 1 && typical > kBins[bin].smem) bin++;
+        }
+        bins[bin].push_back(i);
         if (KS > 0x7FFFFFFFull) { g_last_error = "max_ctr * n_actors too large; re-rank counters densely on the host"; return PT_ERR_INVALID; }
         b->bin_slab[bin] = std::max(b->bin_slab[bin], arena_worst_bytes(L.n_insdel, L.n_mark, KS));
     }
