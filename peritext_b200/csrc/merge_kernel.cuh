@@ -815,10 +815,10 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         for (uint32_t v = tid; v < nvis; v += BLOCK)
             if ((HeadB[v >> 5] >> (v & 31)) & 1u) SpanStart[headRank(v)] = (Idx)v;
         __syncthreads();
-        for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
+        for (uint32_t e = tid >> 5; e < 2 * Mc; e += BLOCK / 32) {       // one warp per piece, lanes over the spans it covers
             uint32_t va = PcA[e], vb = PcB[e];
             if (va >= vb) continue;
-            for (uint32_t j = headRank(va), j1 = headRank(vb); j < j1; j++) atomicAdd(&SpanCC[j], 1u);
+            for (uint32_t j = headRank(va) + lane, j1 = headRank(vb); j < j1; j += 32) atomicAdd(&SpanCC[j], 1u);
         }
         __syncthreads();
         uint32_t totalC;
@@ -847,11 +847,11 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         const uint32_t slBytes = (totalC * 4u + 15u) & ~15u;
         const bool staged = totalC > 0 && A.sm_used + slBytes <= A.sm_cap;
         uint32_t* SL = staged ? reinterpret_cast<uint32_t*>(ptk_smem + A.sm_used) : pool;
-        for (uint32_t e = tid; e < 2 * Mc; e += BLOCK) {
+        for (uint32_t e = tid >> 5; e < 2 * Mc; e += BLOCK / 32) {
             uint32_t va = PcA[e], vb = PcB[e];
             if (va >= vb) continue;
             const uint32_t id = CId[e >> 1];
-            for (uint32_t j = headRank(va), j1 = headRank(vb); j < j1; j++)
+            for (uint32_t j = headRank(va) + lane, j1 = headRank(vb); j < j1; j += 32)
                 SL[SpanCO[j] + atomicAdd(&SpanCur[j], 1u)] = id;
         }
         __syncthreads();
