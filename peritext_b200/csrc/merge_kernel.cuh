@@ -48,6 +48,7 @@ struct BatchParams {
     uint32_t* retry_list;                 // non-null: logs that do not fit this bin's shared memory are deferred here
     uint32_t* retry_count;
     const uint32_t* n_work_dev;           // non-null: number of work items is read from device memory (retry launch)
+    uint32_t prefetch_next;               // prefetch the next log's records into L2 while working on the current one
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -908,7 +909,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : 
         if (threadIdx.x == 0) ctx.work_next = atomicAdd(P.work_counter, 1u);
         __syncthreads();
         const uint32_t wn = ctx.work_next;
-        if (wn < n_work) {
+        if (P.prefetch_next && wn < n_work) {
             const pt_log_desc& Ln = P.desc[P.order[wn]];
             const char* p0 = reinterpret_cast<const char*>(P.insdel + Ln.insdel_off);
             const uint32_t lines = (uint32_t)(((unsigned long long)Ln.n_insdel * sizeof(pt_insdel_rec) + 127) >> 7);
