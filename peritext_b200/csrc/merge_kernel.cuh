@@ -49,6 +49,7 @@ struct BatchParams {
     uint32_t* retry_count;
     const uint32_t* n_work_dev;           // non-null: number of work items is read from device memory (retry launch)
     uint32_t prefetch_next;               // prefetch the next log's records into L2 while working on the current one
+    uint32_t use_tma;                     // stage the record stream through shared memory with cp.async.bulk (shared-only path)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -57,8 +58,35 @@ struct BatchParams {
 __device__ __forceinline__ uint4 ld_rec(const pt_insdel_rec* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ---- TMA (cp.async.bulk, 1-D) + mbarrier helpers: global -> shared staging of the record stream ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 template <int BLOCK>
 struct BlockCtx {
+    unsigned long long tma_bar[2];      // mbarriers of the two staging buffers (initialised once per CTA)
     uint32_t warp_a[32], warp_b[32];
     uint32_t tot_a, tot_b;
     uint32_t status;
@@ -185,7 +213,7 @@ __device__ __forceinline__ unsigned long long node_make(uint32_t nxt, uint32_t w
 // The per-log pipeline.  Idx = uint16_t (logs with < 32000 records) or uint32_t.
 // =========================================================================================================
 template <class Idx, int BLOCK, bool SH>
-__device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>& c) {
+__device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>& c, uint32_t& tma_parity) {
     constexpr Idx NONE = (Idx)~(Idx)0;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
 
@@ -247,6 +275,36 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             const uint32_t insW = __ballot_sync(0xffffffffu, isIns), candW = __ballot_sync(0xffffffffu, cand);
             if (lane == 0 && i < n) { InsBits[i >> 5] = insW; HeadBits[i >> 5] = candW; }
         };
+        if (SH && P.use_tma) {
+            // TMA-staged record stream: chunks of 2*BLOCK records land in a double-buffered shared-memory stage
+            // (cp.async.bulk + mbarrier complete_tx); chunk k+2 is in flight while chunk k is decoded.
+            constexpr uint32_t CH = 2 * BLOCK;
+            const uint32_t stage_mark = A.sm_used;
+            PT_ALLOC(Stage, uint4, 2 * CH);
+            const uint32_t nch = (n + CH - 1) / CH;
+            auto issue = [&](uint32_t k) {
+                const uint32_t b = k & 1u, cnt = min(CH, n - k * CH);
+                mbar_expect_tx(&c.tma_bar[b], cnt * 16u);
+                tma_load_1d(Stage + b * CH, ins + (size_t)k * CH, cnt * 16u, &c.tma_bar[b]);
+            };
+            if (tid == 0) { fence_proxy_async(); if (nch > 0) issue(0); if (nch > 1) issue(1); }
+            for (uint32_t k = 0; k < nch; k++) {
+                const uint32_t b = k & 1u;
+                mbar_wait(&c.tma_bar[b], (tma_parity >> b) & 1u);
+                tma_parity ^= 1u << b;
+                const uint4* st = Stage + b * CH;
+                const uint32_t i0 = k * CH + tid, i1 = i0 + BLOCK;
+                const uint4 r0 = i0 < n ? st[tid] : zero4, r1 = i1 < n ? st[BLOCK + tid] : zero4;
+                uint4 p0 = zero4, p1 = zero4;
+                if (i0 < n) { if (tid > 0) p0 = st[tid - 1]; else if (i0 > 0) p0 = ld_rec(ins + i0 - 1); }
+                if (i1 < n) p1 = st[BLOCK + tid - 1];
+                stepA(i0, r0, p0);
+                stepA(i1, r1, p1);
+                __syncthreads();                                   // everyone is done with buffer b
+                if (tid == 0 && k + 2 < nch) { fence_proxy_async(); issue(k + 2); }
+            }
+            A.sm_used = stage_mark;                                // release the stage
+        } else
         for (uint32_t base = 0; base < n; base += 2 * BLOCK) {     // two records per thread per trip: 4 loads in flight
             const uint32_t i0 = base + tid, i1 = i0 + BLOCK;
             const uint4 r0 = i0 < n ? ld_rec(ins + i0) : zero4, r1 = i1 < n ? ld_rec(ins + i1) : zero4;
@@ -900,7 +958,8 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : BLOCK == 128 ? 7 : BLOCK == 64 ? 8 : BLOCK == 32 ? 8 : 1)) merge_logs_kernel(const BatchParams P) {
     __shared__ BlockCtx<BLOCK> ctx;
     const uint32_t n_work = P.n_work_dev ? *P.n_work_dev : P.n_work;
-    if (threadIdx.x == 0) ctx.work_next = atomicAdd(P.work_counter, 1u);
+    uint32_t tma_parity = 0;                // bit b: parity to wait for on staging barrier b (uniform across the CTA)
+    if (threadIdx.x == 0) { ctx.work_next = atomicAdd(P.work_counter, 1u); mbar_init(&ctx.tma_bar[0], 1); mbar_init(&ctx.tma_bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     for (;;) {
         const uint32_t w = ctx.work_next;
@@ -920,14 +979,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : 
         const bool small = L.n_insdel < 32000u && L.n_mark < 32000u;
         // optimistic: everything in shared memory (LDS/STS); restart with the spill-capable variant if it does not fit
         int spill;
-        if (small) spill = merge_one_log<uint16_t, BLOCK, true>(P, li, ctx); else spill = merge_one_log<uint32_t, BLOCK, true>(P, li, ctx);
+        if (small) spill = merge_one_log<uint16_t, BLOCK, true>(P, li, ctx, tma_parity); else spill = merge_one_log<uint32_t, BLOCK, true>(P, li, ctx, tma_parity);
         if (spill) {
             __syncthreads();
             if (P.retry_list) {            // defer to the next bin (larger shared-memory budget)
                 if (threadIdx.x == 0) { P.retry_list[atomicAdd(P.retry_count, 1u)] = li; atomicAdd(&P.stats[2], 1ull); }
                 continue;
             }
-            if (small) merge_one_log<uint16_t, BLOCK, false>(P, li, ctx); else merge_one_log<uint32_t, BLOCK, false>(P, li, ctx);
+            if (small) merge_one_log<uint16_t, BLOCK, false>(P, li, ctx, tma_parity); else merge_one_log<uint32_t, BLOCK, false>(P, li, ctx, tma_parity);
         }
         if (threadIdx.x == 0) atomicAdd(&P.stats[spill ? 1 : 0], 1ull);
     }
