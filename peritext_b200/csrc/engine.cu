@@ -336,8 +336,8 @@ int pt_batch_merge(pt_batch* b) {
     P.comment_pool = (uint32_t*)b->d_pool.p; P.comment_used = (unsigned long long*)b->d_pool_used.p; P.comment_cap = b->pool_cap;
     P.slab = (char*)b->d_slab.p;
     P.stats = (unsigned long long*)b->d_stats.p;
-    { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 1u; }
-    { const char* e = getenv("PT_TMA"); P.use_tma = e ? (uint32_t)atoi(e) : 0u; }
+    { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 0u; }
+    { const char* e = getenv("PT_TMA"); P.use_tma = e ? (uint32_t)atoi(e) : 1u; }
     int rc;
     // largest logs first: the long-running CTAs start earliest
     // ascending bins; a log whose working set does not fit bin k's shared memory is deferred (on the device) to bin k+1;

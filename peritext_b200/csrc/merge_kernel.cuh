@@ -874,10 +874,13 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         for (uint32_t v = tid; v < nvis; v += BLOCK)
             if ((HeadB[v >> 5] >> (v & 31)) & 1u) SpanStart[headRank(v)] = (Idx)v;
         __syncthreads();
-        for (uint32_t e = tid >> 5; e < 2 * Mc; e += BLOCK / 32) {       // one warp per piece, lanes over the spans it covers
+        // many spans per piece: one warp per piece, lanes over the spans it covers; few spans: one thread per piece
+        const bool wpp = nspans >= 256;
+        const uint32_t pe0 = wpp ? (tid >> 5) : tid, peStep = wpp ? BLOCK / 32 : BLOCK, pj0 = wpp ? lane : 0u, pjStep = wpp ? 32u : 1u;
+        for (uint32_t e = pe0; e < 2 * Mc; e += peStep) {
             uint32_t va = PcA[e], vb = PcB[e];
             if (va >= vb) continue;
-            for (uint32_t j = headRank(va) + lane, j1 = headRank(vb); j < j1; j += 32) atomicAdd(&SpanCC[j], 1u);
+            for (uint32_t j = headRank(va) + pj0, j1 = headRank(vb); j < j1; j += pjStep) atomicAdd(&SpanCC[j], 1u);
         }
         __syncthreads();
         uint32_t totalC;
@@ -906,11 +909,11 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         const uint32_t slBytes = (totalC * 4u + 15u) & ~15u;
         const bool staged = totalC > 0 && A.sm_used + slBytes <= A.sm_cap;
         uint32_t* SL = staged ? reinterpret_cast<uint32_t*>(ptk_smem + A.sm_used) : pool;
-        for (uint32_t e = tid >> 5; e < 2 * Mc; e += BLOCK / 32) {
+        for (uint32_t e = pe0; e < 2 * Mc; e += peStep) {
             uint32_t va = PcA[e], vb = PcB[e];
             if (va >= vb) continue;
             const uint32_t id = CId[e >> 1];
-            for (uint32_t j = headRank(va) + lane, j1 = headRank(vb); j < j1; j += 32)
+            for (uint32_t j = headRank(va) + pj0, j1 = headRank(vb); j < j1; j += pjStep)
                 SL[SpanCO[j] + atomicAdd(&SpanCur[j], 1u)] = id;
         }
         __syncthreads();
