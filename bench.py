@@ -200,7 +200,9 @@ def main():
                          p_ins.numpy()[: batch.insdel.nbytes].view(INSDEL_DT), p_mk.numpy()[: batch.marks.nbytes].view(MARK_DT),
                          batch.values, batch.link_attrs, batch.comment_ids, batch.other_attrs, batch.meta)
 
-    stream = torch.cuda.current_stream()
+    # a non-default stream: the engine captures its launch sequence into a CUDA graph (not possible on the legacy stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng = BatchEngine(local_rank, stream=stream.cuda_stream)
     eng.upload(pbatch)
 

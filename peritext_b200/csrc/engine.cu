@@ -109,13 +109,16 @@ struct pt_batch {
     size_t bin_slab[kNumBins] = {0};
     size_t retry_slab = 0;
     // device
-    DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_pool_used, d_slab, d_stats, d_retry;
+    DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_slab, d_retry;
     const pt_insdel_rec* dp_insdel = nullptr;
     const pt_mark_rec* dp_marks = nullptr;
     // pinned host
     HostBuf h_stage, h_results, h_text, h_spans, h_pool, h_misc;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
+    cudaGraphExec_t graph_exec = nullptr;   // the merge sequence of the current batch, captured once
+    bool graph_ok = false, graph_tried = false;
+    uint32_t kernels_per_merge = 0;
     uint64_t pool_used_host = 0;
 };
 
@@ -193,15 +196,13 @@ int alloc_and_upload_plan(pt_batch* b) {
     const size_t n = b->n_logs;
     if ((rc = b->d_desc.reserve(std::max<size_t>(1, n) * sizeof(pt_log_desc)))) return rc;
     if ((rc = b->d_order.reserve(std::max<size_t>(1, n) * 4))) return rc;
-    if ((rc = b->d_counters.reserve((3 * kNumBins) * 4))) return rc;
+    if ((rc = b->d_counters.reserve(256))) return rc;   // [0,64) stats | [64,72) pool cursor | [128,176) work/deferral counters
     if ((rc = b->d_results.reserve(std::max<size_t>(1, n) * sizeof(pt_log_result)))) return rc;
     if ((rc = b->d_text_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
     if ((rc = b->d_span_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
     if ((rc = b->d_text.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
     if ((rc = b->d_spans.reserve(std::max<uint64_t>(1, b->n_span) * sizeof(pt_span)))) return rc;
     if ((rc = b->d_pool.reserve(std::max<uint64_t>(1, b->pool_cap) * 4))) return rc;
-    if ((rc = b->d_pool_used.reserve(8))) return rc;
-    if ((rc = b->d_stats.reserve(64))) return rc;
     if ((rc = b->d_retry.reserve(std::max<size_t>(1, n) * 4 * kNumBins + 16))) return rc;
     size_t slab_total = 0, slab_max = 0;
     for (int k = 0; k < kNumBins; k++) slab_max = std::max(slab_max, b->bin_slab[k]);
@@ -232,7 +233,7 @@ int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P, bool retry) {
     const BinCfg& cfg = kBins[k];
     uint32_t cnt = retry ? b->n_logs : b->bin_first[k + 1] - b->bin_first[k];
     uint32_t grid = (uint32_t)std::min<size_t>(cnt, (size_t)b->num_sms * cfg.ctas_per_sm);
-    uint32_t* counters = (uint32_t*)b->d_counters.p;
+    uint32_t* counters = (uint32_t*)((char*)b->d_counters.p + 128);
     uint32_t* lists = (uint32_t*)b->d_retry.p;
     if (retry) {
         P.order = lists + (size_t)k * b->n_logs; P.n_work = 0; P.n_work_dev = counters + 2 * kNumBins + k;
@@ -293,6 +294,8 @@ static int upload_common(pt_batch* b, const pt_packed_ops* ops, bool adopt) {
     if (!b || !ops || (ops->n_logs && !ops->logs)) return PT_ERR_INVALID;
     PT_CUDA(cudaSetDevice(b->device));
     b->have_batch = false; b->merged = false;
+    if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
+    b->graph_ok = false; b->graph_tried = false;
     int rc = plan_batch(b, ops);
     if (rc) return rc;
     if ((rc = alloc_and_upload_plan(b))) return rc;
@@ -319,27 +322,20 @@ static int upload_common(pt_batch* b, const pt_packed_ops* ops, bool adopt) {
 int pt_batch_upload(pt_batch* b, const pt_packed_ops* ops) { return upload_common(b, ops, false); }
 int pt_batch_adopt_device(pt_batch* b, const pt_packed_ops* ops) { return upload_common(b, ops, true); }
 
-int pt_batch_merge(pt_batch* b) {
-    if (!b) return PT_ERR_INVALID;
-    if (!b->have_batch) { g_last_error = "pt_batch_merge before pt_batch_upload"; return PT_ERR_STATE; }
-    PT_CUDA(cudaSetDevice(b->device));
-    PT_CUDA(cudaEventRecord(b->ev0, b->stream));
-    PT_CUDA(cudaMemsetAsync(b->d_counters.p, 0, (3 * kNumBins) * 4, b->stream));
-    PT_CUDA(cudaMemsetAsync(b->d_pool_used.p, 0, 8, b->stream));
-    PT_CUDA(cudaMemsetAsync(b->d_stats.p, 0, 64, b->stream));
+static int enqueue_merge(pt_batch* b) {
+    PT_CUDA(cudaMemsetAsync(b->d_counters.p, 0, 256, b->stream));   // stats, pool cursor and queue counters in one shot
     ptk::BatchParams P{};
     P.desc = (const pt_log_desc*)b->d_desc.p;
     P.insdel = b->dp_insdel; P.marks = b->dp_marks;
     P.results = (pt_log_result*)b->d_results.p;
     P.text_off = (const uint64_t*)b->d_text_off.p; P.span_off = (const uint64_t*)b->d_span_off.p;
     P.text = (uint32_t*)b->d_text.p; P.spans = (pt_span*)b->d_spans.p;
-    P.comment_pool = (uint32_t*)b->d_pool.p; P.comment_used = (unsigned long long*)b->d_pool_used.p; P.comment_cap = b->pool_cap;
+    P.comment_pool = (uint32_t*)b->d_pool.p; P.comment_used = (unsigned long long*)((char*)b->d_counters.p + 64); P.comment_cap = b->pool_cap;
     P.slab = (char*)b->d_slab.p;
-    P.stats = (unsigned long long*)b->d_stats.p;
+    P.stats = (unsigned long long*)b->d_counters.p;
     { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 0u; }
     { const char* e = getenv("PT_TMA"); P.use_tma = e ? (uint32_t)atoi(e) : 1u; }
     int rc;
-    // largest logs first: the long-running CTAs start earliest
     // ascending bins; a log whose working set does not fit bin k's shared memory is deferred (on the device) to bin k+1;
     // only the last bin can spill to the global slab
     bool lower = false;
@@ -347,6 +343,41 @@ int pt_batch_merge(pt_batch* b) {
         if ((rc = launch_bin(b, k, P, false))) return rc;
         if (k > 0 && lower && (rc = launch_bin(b, k, P, true))) return rc;
         lower = lower || b->bin_first[k + 1] > b->bin_first[k];
+    }
+    return PT_OK;
+}
+
+int pt_batch_merge(pt_batch* b) {
+    if (!b) return PT_ERR_INVALID;
+    if (!b->have_batch) { g_last_error = "pt_batch_merge before pt_batch_upload"; return PT_ERR_STATE; }
+    PT_CUDA(cudaSetDevice(b->device));
+    // The launch sequence of a batch is fixed: capture it once into a CUDA graph (not possible on the legacy default
+    // stream, where the launches are simply enqueued directly).
+    if (!b->graph_tried) {
+        b->graph_tried = true;
+        const char* eg = getenv("PT_GRAPH");
+        if (b->stream != nullptr && !(eg && atoi(eg) == 0)) {
+            const uint64_t l0 = b->launches;
+            if (cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                int rc = enqueue_merge(b);
+                cudaGraph_t g = nullptr;
+                cudaError_t e = cudaStreamEndCapture(b->stream, &g);
+                if (rc == PT_OK && e == cudaSuccess && g && cudaGraphInstantiate(&b->graph_exec, g, 0) == cudaSuccess) {
+                    b->graph_ok = true; b->kernels_per_merge = (uint32_t)(b->launches - l0);
+                }
+                if (g) cudaGraphDestroy(g);
+                b->launches = l0;
+            }
+            cudaGetLastError();
+        }
+    }
+    PT_CUDA(cudaEventRecord(b->ev0, b->stream));
+    if (b->graph_ok) {
+        PT_CUDA(cudaGraphLaunch(b->graph_exec, b->stream));
+        b->launches += b->kernels_per_merge;
+    } else {
+        int rc = enqueue_merge(b);
+        if (rc) return rc;
     }
     PT_CUDA(cudaEventRecord(b->ev1, b->stream));
     b->merged = true;
@@ -388,7 +419,7 @@ int pt_batch_download(pt_batch* b, pt_spans_view* out) {
     if ((rc = b->h_text.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
     if ((rc = b->h_spans.reserve(std::max<uint64_t>(1, b->n_span) * sizeof(pt_span)))) return rc;
     if ((rc = b->h_misc.reserve(16))) return rc;
-    PT_CUDA(cudaMemcpyAsync(b->h_misc.p, b->d_pool_used.p, 8, cudaMemcpyDeviceToHost, b->stream));
+    PT_CUDA(cudaMemcpyAsync(b->h_misc.p, (char*)b->d_counters.p + 64, 8, cudaMemcpyDeviceToHost, b->stream));
     if (n) PT_CUDA(cudaMemcpyAsync(b->h_results.p, b->d_results.p, n * sizeof(pt_log_result), cudaMemcpyDeviceToHost, b->stream));
     if (b->n_text) PT_CUDA(cudaMemcpyAsync(b->h_text.p, b->d_text.p, b->n_text * 4, cudaMemcpyDeviceToHost, b->stream));
     if (b->n_span) PT_CUDA(cudaMemcpyAsync(b->h_spans.p, b->d_spans.p, b->n_span * sizeof(pt_span), cudaMemcpyDeviceToHost, b->stream));
@@ -426,7 +457,7 @@ int pt_batch_stats(pt_batch* b, uint64_t out[4]) {
     if (!b || !out) return PT_ERR_INVALID;
     if (!b->merged) return PT_ERR_STATE;
     unsigned long long h[8] = {0};
-    PT_CUDA(cudaMemcpyAsync(h, b->d_stats.p, 32, cudaMemcpyDeviceToHost, b->stream));
+    PT_CUDA(cudaMemcpyAsync(h, b->d_counters.p, 32, cudaMemcpyDeviceToHost, b->stream));
     PT_CUDA(cudaStreamSynchronize(b->stream));
     for (int i = 0; i < 4; i++) out[i] = h[i];
     return PT_OK;
@@ -437,10 +468,11 @@ void pt_batch_destroy(pt_batch* b) {
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
-                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_pool_used, &b->d_slab, &b->d_stats, &b->d_retry}) d->release();
+                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_slab, &b->d_retry}) d->release();
     for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc}) h->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
     delete b;
 }
 

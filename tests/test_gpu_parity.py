@@ -124,3 +124,25 @@ def test_error_status_element_not_found(engine):
     ref, _ = replay_packed(bad)
     assert got.results["status"].tolist() == [1, 0] == ref.results["status"].tolist()   # src/micromerge.ts:752
     assert got.canonical(1) == ref.canonical(1)
+
+
+def test_cuda_graph_path_on_a_user_stream():
+    """On a non-default stream the engine replays its launch sequence as a CUDA graph; results must not change,
+    also across re-uploads of different batches on one handle."""
+    import torch
+    from peritext_b200.engine import BatchEngine
+    s = torch.cuda.Stream()
+    eng = BatchEngine(0, stream=s.cuda_stream)
+    for seed0 in (500, 600):
+        logs = []
+        for seed in range(6):
+            _, lg, _ = fuzz_session(OracleMicromerge, seed0 + seed, 100)
+            logs += lg
+        batch = pack_logs(logs)
+        eng.upload(batch)
+        for _ in range(3):
+            eng.merge()
+        got = eng.download()
+        ref, _ = replay_packed(batch, threads=2)
+        assert_batch_equal(batch, got, ref)
+    eng.close()
