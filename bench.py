@@ -36,17 +36,31 @@ UNIT = "ops/s"
 
 
 def sample_clocks(stop_evt, out, device_index):
+    """One long-running `nvidia-smi -lms 100` (the B200_PROFILING.md clocks line) read until the bench is done."""
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    while not stop_evt.is_set():
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device_index)],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+    import select
+    try:
+        while not stop_evt.is_set():
+            r, _, _ = select.select([p.stdout], [], [], 0.1)
+            if r:
+                line = p.stdout.readline()
+                if not line:
+                    break
+                parts = [x.strip() for x in line.strip().split(",")]
+                if len(parts) >= 9:
+                    out.append(parts)
+    finally:
+        p.terminate()
         try:
-            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(device_index)],
-                               capture_output=True, text=True, timeout=5)
-            if r.returncode == 0 and r.stdout.strip():
-                out.append([x.strip() for x in r.stdout.strip().split(",")])
+            p.wait(timeout=2)
         except Exception:
-            pass
-        stop_evt.wait(0.2)
+            p.kill()
 
 
 def clocks_summary(samples):
