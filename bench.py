@@ -36,31 +36,20 @@ UNIT = "ops/s"
 
 
 def sample_clocks(stop_evt, out, device_index):
-    """One long-running `nvidia-smi -lms 100` (the B200_PROFILING.md clocks line) read until the bench is done."""
+    """Polls the B200_PROFILING.md clocks line (one nvidia-smi query per sample, back to back) while the bench runs."""
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    try:
-        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device_index)],
-                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-    except Exception:
-        return
-    import select
-    try:
-        while not stop_evt.is_set():
-            r, _, _ = select.select([p.stdout], [], [], 0.1)
-            if r:
-                line = p.stdout.readline()
-                if not line:
-                    break
-                parts = [x.strip() for x in line.strip().split(",")]
+    while not stop_evt.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(device_index)],
+                               capture_output=True, text=True, timeout=5)
+            if r.returncode == 0 and r.stdout.strip():
+                parts = [x.strip() for x in r.stdout.strip().split(",")]
                 if len(parts) >= 9:
                     out.append(parts)
-    finally:
-        p.terminate()
-        try:
-            p.wait(timeout=2)
         except Exception:
-            p.kill()
+            pass
+        stop_evt.wait(0.02)
 
 
 def clocks_summary(samples):
@@ -231,14 +220,13 @@ def main():
         if world > 1:
             dist.all_gather_into_tensor(gathered, res_dev)   # the path's only exchange: digests for the convergence check
 
+    stop_evt, samples = threading.Event(), []
+    th = threading.Thread(target=sample_clocks, args=(stop_evt, samples, local_rank), daemon=True)
+    th.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     launches0 = eng.launch_count
-
-    stop_evt, samples = threading.Event(), []
-    th = threading.Thread(target=sample_clocks, args=(stop_evt, samples, local_rank), daemon=True)
-    th.start()
     # keep the GPU busy for a moment so the clock sampler sees the loaded state as well
     if world > 1:
         dist.barrier()
