@@ -144,13 +144,19 @@ typedef struct pt_spans_view {
     const pt_span* spans;
     const uint32_t* comment_pool;
     uint64_t comment_pool_used;
+    const uint32_t* seq;          /* NULL unless PT_FLAG_EMIT_SEQUENCE: per log (offset text_off[i], n_elems entries) the element
+                                     sequence incl. tombstones (the reference's `metadata` array, src/micromerge.ts:255):
+                                     bits30:0 = index of the element's insert record in the log's ins/del records,
+                                     bit31 = deleted                                                                  */
 } pt_spans_view;
 
 /* Engine limits / tuning. Zero-initialise for defaults. */
 typedef struct pt_limits {
-    uint64_t comment_pool_entries; /* 0: 4 x number of comment mark ops in the batch (+slack)     */
-    uint32_t reserved[6];
+    uint64_t comment_pool_entries; /* 0: 64 x number of mark ops in the batch (+slack)            */
+    uint32_t flags;                /* PT_FLAG_*                                                     */
+    uint32_t reserved[5];
 } pt_limits;
+#define PT_FLAG_EMIT_SEQUENCE 1u   /* also emit the element sequence (needed by op generation / cursors on the host) */
 
 typedef enum pt_status {
     PT_OK = 0,

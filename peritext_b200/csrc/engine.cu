@@ -109,11 +109,11 @@ struct pt_batch {
     size_t bin_slab[kNumBins] = {0};
     size_t retry_slab = 0;
     // device
-    DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_slab, d_retry;
+    DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_slab, d_retry, d_seq;
     const pt_insdel_rec* dp_insdel = nullptr;
     const pt_mark_rec* dp_marks = nullptr;
     // pinned host
-    HostBuf h_stage, h_results, h_text, h_spans, h_pool, h_misc;
+    HostBuf h_stage, h_results, h_text, h_spans, h_pool, h_misc, h_seq;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     cudaGraphExec_t graph_exec = nullptr;   // the merge sequence of the current batch, captured once
@@ -201,6 +201,7 @@ int alloc_and_upload_plan(pt_batch* b) {
     if ((rc = b->d_text_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
     if ((rc = b->d_span_off.reserve(std::max<size_t>(1, n) * 8))) return rc;
     if ((rc = b->d_text.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
+    if ((b->limits.flags & PT_FLAG_EMIT_SEQUENCE) && (rc = b->d_seq.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
     if ((rc = b->d_spans.reserve(std::max<uint64_t>(1, b->n_span) * sizeof(pt_span)))) return rc;
     if ((rc = b->d_pool.reserve(std::max<uint64_t>(1, b->pool_cap) * 4))) return rc;
     if ((rc = b->d_retry.reserve(std::max<size_t>(1, n) * 4 * kNumBins + 16))) return rc;
@@ -332,6 +333,7 @@ static int enqueue_merge(pt_batch* b) {
     P.text = (uint32_t*)b->d_text.p; P.spans = (pt_span*)b->d_spans.p;
     P.comment_pool = (uint32_t*)b->d_pool.p; P.comment_used = (unsigned long long*)((char*)b->d_counters.p + 64); P.comment_cap = b->pool_cap;
     P.slab = (char*)b->d_slab.p;
+    P.seq = (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) ? (uint32_t*)b->d_seq.p : nullptr;
     P.stats = (unsigned long long*)b->d_counters.p;
     { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 0u; }
     { const char* e = getenv("PT_TMA"); P.use_tma = e ? (uint32_t)atoi(e) : 1u; }
@@ -423,6 +425,11 @@ int pt_batch_download(pt_batch* b, pt_spans_view* out) {
     if (n) PT_CUDA(cudaMemcpyAsync(b->h_results.p, b->d_results.p, n * sizeof(pt_log_result), cudaMemcpyDeviceToHost, b->stream));
     if (b->n_text) PT_CUDA(cudaMemcpyAsync(b->h_text.p, b->d_text.p, b->n_text * 4, cudaMemcpyDeviceToHost, b->stream));
     if (b->n_span) PT_CUDA(cudaMemcpyAsync(b->h_spans.p, b->d_spans.p, b->n_span * sizeof(pt_span), cudaMemcpyDeviceToHost, b->stream));
+    const bool want_seq = (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) != 0;
+    if (want_seq) {
+        if ((rc = b->h_seq.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
+        if (b->n_text) PT_CUDA(cudaMemcpyAsync(b->h_seq.p, b->d_seq.p, b->n_text * 4, cudaMemcpyDeviceToHost, b->stream));
+    }
     PT_CUDA(cudaStreamSynchronize(b->stream));
     uint64_t used = *(unsigned long long*)b->h_misc.p;
     if (used > b->pool_cap) used = b->pool_cap;
@@ -440,6 +447,7 @@ int pt_batch_download(pt_batch* b, pt_spans_view* out) {
     out->spans = (const pt_span*)b->h_spans.p;
     out->comment_pool = (const uint32_t*)b->h_pool.p;
     out->comment_pool_used = used;
+    out->seq = want_seq ? (const uint32_t*)b->h_seq.p : nullptr;
     return PT_OK;
 }
 
@@ -468,8 +476,8 @@ void pt_batch_destroy(pt_batch* b) {
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
-                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_slab, &b->d_retry}) d->release();
-    for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc}) h->release();
+                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_slab, &b->d_retry, &b->d_seq}) d->release();
+    for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc, &b->h_seq}) h->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);

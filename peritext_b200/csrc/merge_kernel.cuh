@@ -50,6 +50,7 @@ struct BatchParams {
     const uint32_t* n_work_dev;           // non-null: number of work items is read from device memory (retry launch)
     uint32_t prefetch_next;               // prefetch the next log's records into L2 while working on the current one
     uint32_t use_tma;                     // stage the record stream through shared memory with cp.async.bulk (shared-only path)
+    uint32_t* seq;                        // optional: element sequence output (record index | deleted << 31), text offsets
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -223,6 +224,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     const pt_insdel_rec* __restrict__ ins = P.insdel + L.insdel_off;
     const pt_mark_rec* __restrict__ mk = P.marks + L.mark_off;
     uint32_t* text_out = P.text + P.text_off[li];
+    uint32_t* seq_out = P.seq ? P.seq + P.text_off[li] : nullptr;
     pt_span* span_out = P.spans + P.span_off[li];
     pt_log_result* res = P.results + li;
 
@@ -554,6 +556,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         auto stepF = [&](uint32_t i, bool live, const uint4 r) {
             if (!live) return;
             if ((uint32_t)T[keyOf(r.x, r.z & 0xFFFFu)] != i) fail(PT_LOG_BAD_OPID);     // two inserts with one opId
+            if (seq_out) seq_out[posOf(i)] = i | (isVis(i) ? 0u : 0x80000000u);
             if (!isVis(i)) return;
             const uint32_t tok = PT_PAYLOAD_TOKEN(r.w);
             const uint32_t vr = visOf(i);

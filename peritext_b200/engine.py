@@ -34,11 +34,14 @@ class _PackedOps(ctypes.Structure):
 class _SpansView(ctypes.Structure):
     _fields_ = [("n_logs", ctypes.c_uint32), ("results", ctypes.c_void_p), ("text_off", ctypes.c_void_p),
                 ("span_off", ctypes.c_void_p), ("text", ctypes.c_void_p), ("spans", ctypes.c_void_p),
-                ("comment_pool", ctypes.c_void_p), ("comment_pool_used", ctypes.c_uint64)]
+                ("comment_pool", ctypes.c_void_p), ("comment_pool_used", ctypes.c_uint64), ("seq", ctypes.c_void_p)]
 
 
 class _Limits(ctypes.Structure):
-    _fields_ = [("comment_pool_entries", ctypes.c_uint64), ("reserved", ctypes.c_uint32 * 6)]
+    _fields_ = [("comment_pool_entries", ctypes.c_uint64), ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 5)]
+
+
+FLAG_EMIT_SEQUENCE = 1
 
 
 def load_library() -> ctypes.CDLL:
@@ -78,11 +81,11 @@ def _check(rc: int, what: str):
 class BatchEngine:
     """One handle per (GPU, batch).  ``upload`` -> ``merge`` -> ``download``."""
 
-    def __init__(self, device: int = 0, stream: int | None = None, comment_pool_entries: int = 0):
+    def __init__(self, device: int = 0, stream: int | None = None, comment_pool_entries: int = 0, emit_sequence: bool = False):
         L = load_library()
         self._L = L
         self._h = ctypes.c_void_p()
-        lim = _Limits(comment_pool_entries, (ctypes.c_uint32 * 6)())
+        lim = _Limits(comment_pool_entries, FLAG_EMIT_SEQUENCE if emit_sequence else 0, (ctypes.c_uint32 * 5)())
         _check(L.pt_batch_create(device, ctypes.byref(lim), ctypes.c_void_p(stream or 0), ctypes.byref(self._h)), "pt_batch_create")
         self._keep = None
         self.n_logs = 0
@@ -156,8 +159,10 @@ class BatchEngine:
             n_span = int(span_off[-1]) + int(results[-1]["n_spans"])
         else:
             n_span = 0
+        n_seq = (int(text_off[-1]) + int(results[-1]["n_elems"])) if (n and v.seq) else 0
         return MergedBatch(results, text_off, span_off, arr(v.text, n_text, np.uint32), arr(v.spans, n_span, SPAN_DT),
-                           arr(v.comment_pool, int(v.comment_pool_used), np.uint32))
+                           arr(v.comment_pool, int(v.comment_pool_used), np.uint32),
+                           arr(v.seq, n_seq, np.uint32) if v.seq else None)
 
     def run(self, batch: PackedBatch) -> MergedBatch:
         self.upload(batch); self.merge(); return self.download()

@@ -1,25 +1,45 @@
-"""`Micromerge` facade over the batch engine — the reference's class surface (reference src/micromerge.ts:262) for the
-hot path: `applyChange` (:499) buffers the change after the reference's causal admission checks, and
-`getTextWithFormatting` (:516) materialises the document on the GPU through the C-ABI.
+"""`Micromerge` facade over the batch engine — the reference's class surface (reference src/micromerge.ts:262).
 
-Not built in round 1 (SURVEY.md §8f "next" rows): the Patch stream returned by `applyChange` (an empty list is returned)
-and local op generation `change()` / cursors, which need the materialised element order on the host.
+* `applyChange` (:499) runs the reference's causal admission checks and buffers the change (the op log).
+* `getTextWithFormatting` (:516) / `root` (:290) materialise the document on the GPU through the C-ABI.
+* `change` (:308), `getCursor` / `resolveCursor` (:465/:475) — SURVEY.md §8(f) rows 2 and 4 — are generated on the host
+  from the element sequence the engine emits (`PT_FLAG_EMIT_SEQUENCE`): visible index -> elemId with
+  `lookAfterTombstones` (:762-805) and `changeMark`'s boundary choice (reference src/peritext.ts:458-501).  Local ops are
+  applied to the host mirror incrementally (their opIds are larger than everything known, so they land right after their
+  reference element); remote changes invalidate the mirror and the next access re-materialises on the GPU.
+
+Not built yet: the Patch stream — `applyChange` and `change` return `patches == []`.
 """
 from __future__ import annotations
 
 import copy
 
-from .packing import RangeError, decode_spans, pack_logs, parse_op_id, token_str
+from .packing import (KIND_INSERT, RangeError, TOKEN_POOLED, _root_text_list, decode_spans, js_key, pack_logs,
+                      parse_op_id, token_str)
 
 _default_engine = None
+INCLUSIVE = {"strong": True, "em": True, "comment": False, "link": False}   # markSpec.inclusive, reference src/schema.ts:45-96
 
 
 def default_engine():
     global _default_engine
     if _default_engine is None:
         from .engine import BatchEngine
-        _default_engine = BatchEngine(0)
+        _default_engine = BatchEngine(0, emit_sequence=True)
     return _default_engine
+
+
+def compareOpIds(id1: str, id2: str) -> int:
+    """reference src/micromerge.ts:812-827"""
+    if id1 == id2:
+        return 0
+    c1, a1 = parse_op_id(id1)
+    c2, a2 = parse_op_id(id2)
+    return -1 if (c1 < c2 or (c1 == c2 and js_key(a1) < js_key(a2))) else 1
+
+
+class JsError(Exception):
+    """JS Error thrown by the reference (non-Range)."""
 
 
 class Micromerge:
@@ -28,11 +48,14 @@ class Micromerge:
     def __init__(self, actorId: str, engine=None):
         self.actorId = actorId
         self.clock: dict[str, int] = {}       # :273
+        self._seq = 0                         # :269
         self._maxOp = 0                       # :271
         self._applied: list[dict] = []        # arrival order == the packed log
-        self._objects = {"_root"}             # object ids created so far (makeList / makeMap), :541-547
+        self._objects = {"_root": "map"}      # object id -> kind (:275-281, 541-547)
         self._engine = engine
-        self._cache = None
+        self._cache = None                    # (batch, merged) of the last GPU materialisation
+        self._mirror = None                   # host mirror of the text list: [[elemId, deleted, hasAfter, value], ...]
+        self._mirror_list = None
 
     # -- reference src/micromerge.ts:499-514 --------------------------------------------------------------------------
     def applyChange(self, change: dict) -> list:
@@ -46,18 +69,20 @@ class Micromerge:
             obj = op.get("obj") or "_root"
             if obj not in self._objects:
                 raise RangeError(f"Object does not exist: {obj}")
-            if op["action"] in ("makeList", "makeMap"):
-                self._objects.add(op["opId"])
             parse_op_id(op["opId"])
+        for op in change["ops"]:
+            if op["action"] in ("makeList", "makeMap"):
+                self._objects[op["opId"]] = "list" if op["action"] == "makeList" else "map"
         self.clock[change["actor"]] = change["seq"]
         self._maxOp = max(self._maxOp, change["startOp"] + len(change["ops"]) - 1)
         self._applied.append(copy.deepcopy(change))                  # Change objects passed in are not mutated
         self._cache = None
+        self._mirror = None
         return []   # Patch[]: SURVEY.md §8(f) row 1 — not derived by the batch engine yet
 
-    def change(self, ops):
-        raise NotImplementedError("change() (local op generation, reference src/micromerge.ts:308) is a SURVEY.md §8(f) "
-                                  "'next' row; generate Change objects with the reference or the test oracle")
+    # -- GPU materialisation --------------------------------------------------------------------------------------------
+    def _text_list_id(self):
+        return _root_text_list(self._applied)
 
     def _materialise(self):
         if self._cache is None:
@@ -66,22 +91,174 @@ class Micromerge:
             self._cache = (batch, eng.run(batch))
         return self._cache
 
+    def _meta(self):
+        """Host mirror of the reference's `metadata[textList]` (+ the visible values)."""
+        lid = self._text_list_id()
+        if self._mirror is not None and self._mirror_list == lid:
+            return self._mirror
+        batch, merged = self._materialise()
+        if int(merged.results[0]["status"]) != 0:
+            raise RangeError("List element not found")
+        if merged.seq is None:
+            raise JsError("engine was created without emit_sequence; change()/cursors need the element sequence")
+        ins, _ = batch.log_slice(0)
+        actors = batch.log_actors[0]
+        after_defined = set()      # elements whose markOpsAfter slot is defined: some applied op ends `after` them (peritext.ts:239-241)
+        for ch in self._applied:
+            for op in ch["ops"]:
+                if op.get("obj") == lid and op["action"] in ("addMark", "removeMark") and op["end"]["type"] == "after":
+                    after_defined.add(op["end"]["elemId"])
+        mirror = []
+        for e in merged.sequence(0):
+            r = ins[int(e) & 0x7FFFFFFF]
+            eid = f"{int(r['ctr'])}@{actors[int(r['actor'])]}"
+            tok = int(r["payload"]) & 0x3FFFFFFF
+            mirror.append([eid, bool(int(e) >> 31), eid in after_defined, token_str(tok, batch.values)])
+        self._mirror, self._mirror_list = mirror, lid
+        return mirror
+
+    # -- reference src/micromerge.ts:762-805 ------------------------------------------------------------------------------
+    @staticmethod
+    def _getListElementId(meta, index: int, lookAfterTombstones: bool = False) -> str:
+        visible = -1
+        for metaIndex, element in enumerate(meta):
+            if not element[1]:
+                visible += 1
+                if visible == index:
+                    if lookAfterTombstones:
+                        elemIndex, peek, latest = metaIndex, metaIndex + 1, 0
+                        while peek < len(meta) and meta[peek][1]:
+                            if meta[peek][2]:
+                                latest = peek
+                            peek += 1
+                        if latest:
+                            elemIndex = latest
+                        return meta[elemIndex][0]
+                    return element[0]
+        raise RangeError(f"List index out of bounds: {index}")
+
+    def _findListElement(self, meta, elemId: str):
+        """reference src/micromerge.ts:731-755 -> (index, visible)"""
+        visible = 0
+        for index, element in enumerate(meta):
+            if element[0] == elemId:
+                return index, visible
+            if not element[1]:
+                visible += 1
+        raise RangeError(f"List element not found: {elemId}")
+
+    # -- local op application to the mirror (reference applyListInsert :614-672, applyListUpdate :677-724, marks) --------
+    def _apply_local(self, meta, op):
+        if op["action"] == "set":
+            if op["elemId"] == "_head":
+                index = 0
+            else:
+                index = self._findListElement(meta, op["elemId"])[0] + 1
+            while index < len(meta) and compareOpIds(op["opId"], meta[index][0]) < 0:
+                index += 1
+            meta.insert(index, [op["opId"], False, False, op["value"]])
+        elif op["action"] == "del":
+            meta[self._findListElement(meta, op["elemId"])[0]][1] = True
+        else:
+            if op["end"]["type"] == "after":
+                meta[self._findListElement(meta, op["end"]["elemId"])[0]][2] = True
+
+    # -- reference src/micromerge.ts:308-441 ------------------------------------------------------------------------------
+    def change(self, ops: list[dict]) -> dict:
+        deps = dict(self.clock)
+        self._seq += 1
+        self.clock[self.actorId] = self._seq
+        change = {"actor": self.actorId, "seq": self._seq, "deps": deps, "startOp": self._maxOp + 1, "ops": []}
+        self._applied.append(change)       # ops are appended as they are generated (makeNewOp applies each op at once, :483-493)
+        self._cache = None
+
+        def make(op):
+            self._maxOp += 1
+            op = {"opId": f"{self._maxOp}@{self.actorId}", **op}
+            change["ops"].append(op)
+            return op
+
+        for inputOp in ops:
+            path = list(inputOp.get("path") or [])
+            if path == []:
+                objId, kind = "_root", "map"
+            elif path == ["text"]:
+                objId = self._text_list_id()
+                if objId is None:
+                    raise JsError("Child not found: text in _root")
+                kind = self._objects.get(objId, "list")
+            else:
+                raise RangeError(f"No object at path {path!r}")
+            action = inputOp["action"]
+            if kind == "list":
+                meta = self._meta()
+                visible_len = sum(1 for e in meta if not e[1])
+                if action == "insert":
+                    elemId = "_head" if inputOp["index"] == 0 else self._getListElementId(meta, inputOp["index"] - 1, True)
+                    for value in inputOp["values"]:
+                        if not isinstance(value, str):
+                            raise JsError("Expected value inserted into text to be a string")
+                        op = make({"action": "set", "obj": objId, "elemId": elemId, "insert": True, "value": value})
+                        self._apply_local(meta, op)
+                        elemId = op["opId"]
+                elif action == "delete":
+                    for _ in range(inputOp["count"]):
+                        op = make({"action": "del", "obj": objId, "elemId": self._getListElementId(meta, inputOp["index"])})
+                        self._apply_local(meta, op)
+                elif action in ("addMark", "removeMark"):
+                    mt = inputOp["markType"]
+                    start = {"type": "before", "elemId": self._getListElementId(meta, inputOp["startIndex"])}      # peritext.ts:488
+                    if INCLUSIVE[mt] and inputOp["endIndex"] >= visible_len:
+                        end = {"type": "endOfText"}                                                                 # :491-492
+                    elif INCLUSIVE[mt]:
+                        end = {"type": "before", "elemId": self._getListElementId(meta, inputOp["endIndex"])}       # :494
+                    else:
+                        end = {"type": "after", "elemId": self._getListElementId(meta, inputOp["endIndex"] - 1)}    # :496
+                    body = {"action": action, "obj": objId, "start": start, "end": end, "markType": mt}
+                    if inputOp.get("attrs"):
+                        body["attrs"] = inputOp["attrs"]
+                    op = make(body)
+                    self._apply_local(meta, op)
+                elif action == "del":
+                    raise JsError("Use the remove action")
+                else:
+                    raise JsError("Unimplemented")
+            else:
+                if action in ("makeList", "makeMap", "del"):
+                    op = make({"action": action, "obj": objId, "key": inputOp["key"]})
+                    if action != "del":
+                        self._objects[op["opId"]] = "list" if action == "makeList" else "map"
+                    self._mirror = None
+                elif action == "set":
+                    make({"action": "set", "obj": objId, "key": inputOp["key"], "value": inputOp.get("value")})
+                else:
+                    raise JsError(f"Not a list: {path}")
+        self._cache = None                 # the GPU materialisation (if any) predates the ops generated above
+        return {"change": copy.deepcopy(change), "patches": []}
+
+    # -- reference src/micromerge.ts:465-477 ------------------------------------------------------------------------------
+    def getCursor(self, path, index: int) -> dict:
+        return {"objectId": self._text_list_id(), "elemId": self._getListElementId(self._meta(), index)}
+
+    def resolveCursor(self, cursor: dict) -> int:
+        return self._findListElement(self._meta(), cursor["elemId"])[1]
+
     # -- reference src/micromerge.ts:516-529 -> src/peritext.ts:337 ----------------------------------------------------
     def getTextWithFormatting(self, path=("text",)) -> list[dict]:
         if list(path) != ["text"]:
             raise RangeError(f"No object at path {list(path)!r}")
-        from .packing import _root_text_list
-        if _root_text_list(self._applied) is None:
-            raise KeyError("Child not found: text in _root")         # :458
+        if self._text_list_id() is None:
+            raise JsError("Child not found: text in _root")          # :458
         batch, merged = self._materialise()
         return decode_spans(batch, merged, 0)
 
     @property
     def root(self) -> dict:
         """`{text: [...visible values]}` (reference :290; fuzz.ts:33 and the tests read `root.text`)."""
-        from .packing import _root_text_list
-        if _root_text_list(self._applied) is None:
+        if self._text_list_id() is None:
             return {}
+        if self._mirror is not None and self._mirror_list == self._text_list_id():
+            return {"text": [e[3] for e in self._mirror if not e[1]]}
         batch, merged = self._materialise()
         if int(merged.results[0]["status"]) != 0:
             raise RangeError("List element not found")

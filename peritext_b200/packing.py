@@ -72,6 +72,7 @@ class PackedBatch:
     comment_ids: list[Any] = field(default_factory=list)   # comment rank -> attrs object ({"id": ...}), JS id order
     other_attrs: list[Any] = field(default_factory=list)   # strong/em attrs (normally none)
     meta: dict = field(default_factory=dict)
+    log_actors: list[list[str]] = field(default_factory=list)   # per log: actor rank -> actorId
 
     @property
     def n_logs(self) -> int:
@@ -265,7 +266,8 @@ def pack_logs(logs: Sequence[Sequence[dict]], *, list_ids: Sequence[str | None] 
                              sb[1], eb[1], rank[sb[2]] if sb[2] is not None else 0,
                              rank[eb[2]] if eb[2] is not None else 0, attr, arrival, 0)
         io += len(b.insdel); mo += len(b.marks)
-    return PackedBatch(desc, insdel, marks, values, link_attrs, [comment_objs[c] for c in comment_sorted], other_attrs)
+    return PackedBatch(desc, insdel, marks, values, link_attrs, [comment_objs[c] for c in comment_sorted], other_attrs,
+                       log_actors=[sorted(b.actors, key=js_key) for b in builders])
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -280,6 +282,10 @@ class MergedBatch:
     text: np.ndarray           # u32 tokens
     spans: np.ndarray          # SPAN_DT
     comment_pool: np.ndarray   # u32
+    seq: np.ndarray | None = None   # u32 per element (record index | deleted << 31), only with emit_sequence
+
+    def sequence(self, i: int) -> np.ndarray:
+        o = int(self.text_off[i]); return self.seq[o: o + int(self.results[i]["n_elems"])]
 
     def tokens(self, i: int) -> np.ndarray:
         o = int(self.text_off[i]); return self.text[o: o + int(self.results[i]["n_visible"])]
