@@ -65,14 +65,15 @@ class Micromerge:
         for actor, dep in (change.get("deps") or {}).items():
             if not self.clock.get(actor) or self.clock[actor] < dep:
                 raise RangeError(f"Missing dependency: change {dep} by actor {actor}")
-        for op in change["ops"]:                                     # :538-540, checked before buffering
+        created = {}
+        for op in change["ops"]:                                     # :538-547, validated in op order before buffering
             obj = op.get("obj") or "_root"
-            if obj not in self._objects:
+            if obj not in self._objects and obj not in created:
                 raise RangeError(f"Object does not exist: {obj}")
             parse_op_id(op["opId"])
-        for op in change["ops"]:
             if op["action"] in ("makeList", "makeMap"):
-                self._objects[op["opId"]] = "list" if op["action"] == "makeList" else "map"
+                created[op["opId"]] = "list" if op["action"] == "makeList" else "map"
+        self._objects.update(created)
         self.clock[change["actor"]] = change["seq"]
         self._maxOp = max(self._maxOp, change["startOp"] + len(change["ops"]) - 1)
         self._applied.append(copy.deepcopy(change))                  # Change objects passed in are not mutated
