@@ -76,6 +76,7 @@ size_t arena_worst_bytes(uint64_t n, uint64_t m, uint64_t KS) {
     A(2 * n + 3, 8); A((2 * n + 9) / 8 + 3, 8);                                    // Node Sub
     A(n + 1, I); A(n + 2, 4); A(n + 2, 4); A(n + 1, I); A(n + 1, 4); A(n + 2, I);  // RunHead PosBase VisBase Prun Key GrpOff
     A(n + 1, I); A(n + 1, I); A(n + 1, I);                                         // Unsorted Sorted SPos
+    A(n / 33 + 2, I); A(KS / 32 + 2, 4); A(KS / 32 + 2, I);                        // BigList GBits GPre
     if (m) {
         const uint64_t KW = KS / 32 + 2, S = 2 * m + 2, Mc = m, nsp = 2 * m + 1, NWp = (n + 32) / 32 + 1;
         A(KW + 1, 4); A(KW + 1, I); for (int k = 0; k < 6; k++) A(m + 1, I);       // KBits KPre ByRank MRank IvA IvB IvVA IvVB

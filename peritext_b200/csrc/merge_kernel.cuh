@@ -232,7 +232,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     A.sm_cap = P.smem_arena_bytes; A.sm_used = 0;
     A.gm = P.slab + (unsigned long long)blockIdx.x * P.slab_bytes; A.gm_cap = P.slab_bytes; A.gm_used = 0; A.overflow = false;
 
-    if (tid == 0) { c.status = 0; c.misc[0] = 0; c.misc[2] = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
+    if (tid == 0) { c.status = 0; c.misc[0] = 0; c.misc[2] = 0; c.misc[3] = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
 
     auto keyOf = [&](uint32_t ctr, uint32_t actor) -> uint32_t { return (ctr - 1u) * R + actor; };
     auto badId = [&](uint32_t ctr, uint32_t actor) -> bool { return ctr - 1u >= C || actor >= R; };
@@ -258,6 +258,14 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     fill<uint8_t, BLOCK>(Del, NWr * 32 + 32, (uint8_t)0);
     if (tid == 0) { InsBits[NWr - 1] = 0; HeadBits[NWr - 1] = 0; }
     __syncthreads();
+
+    if (m) {   // number of comment mark ops (sizes the comment tables); issued first so the marks' HBM latency overlaps phase A
+        uint32_t ccnt = 0;
+        for (uint32_t k = tid; k < m; k += BLOCK) ccnt += (((uint32_t)mk[k].kind >> 1) & 3u) == PT_MARK_COMMENT ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ccnt += __shfl_xor_sync(0xffffffffu, ccnt, o);
+        if (lane == 0 && ccnt) atomicAdd(&c.misc[2], ccnt);
+    }
 
     // ---- A: id table + insert / chain-continuation bitmaps (first and only HBM read of the records) ------------
     // cand(i): record i is an insert whose reference element is the insert at record i-1 (a typing chain link)
@@ -369,13 +377,11 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     A.sm_used = mark_sm; A.gm_used = mark_gm;      // release Other / Del
     uint32_t N = 0;
     {
-        uint32_t cnt = 0, ccnt = 0;
+        uint32_t cnt = 0;
         for (uint32_t w = tid; w < NWr; w += BLOCK) cnt += __popc(InsBits[w]);
-        for (uint32_t k = tid; k < m; k += BLOCK) ccnt += (((uint32_t)mk[k].kind >> 1) & 3u) == PT_MARK_COMMENT ? 1u : 0u;   // sizes the comment tables
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); ccnt += __shfl_xor_sync(0xffffffffu, ccnt, o); }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0 && cnt) atomicAdd(&c.misc[0], cnt);
-        if (lane == 0 && ccnt) atomicAdd(&c.misc[2], ccnt);
     }
     __syncthreads();
     N = c.misc[0];
@@ -395,7 +401,8 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         auto al = [](unsigned long long b) -> unsigned long long { return (b + 15ull) & ~15ull; };
         const unsigned long long I = sizeof(Idx);
         const unsigned long long base = (unsigned long long)A.sm_used + 2 * al((M + 2) * 4ull);
-        unsigned long long peak = base + al((E + 1) * 8ull) + al(((E + 7) / 8 + 3) * 8ull) + 5 * al((M + 1) * I) + al((M + 1) * 4ull) + al((M + 2) * I);
+        unsigned long long peak = base + al((E + 1) * 8ull) + al(((E + 7) / 8 + 3) * 8ull) + 5 * al((M + 1) * I) + al((M + 1) * 4ull) + al((M + 2) * I)
+                                 + al((M / 33 + 2) * I) + al(((KS + 31) / 32 + 1) * 4ull) + al(((KS + 31) / 32 + 1) * I);
         if (m) {
             const unsigned long long NWp_ = (N + 32) / 32 + 1, KW_ = (KS + 31) / 32;
             const unsigned long long Sb = (2ull * m + 2 < (unsigned long long)N + 2 ? 2ull * m + 2 : (unsigned long long)N + 2) + 1;
@@ -428,6 +435,9 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     PT_ALLOC(Unsorted, Idx, M + 1);
     PT_ALLOC(Sorted, Idx, M + 1);
     PT_ALLOC(SPos, Idx, M + 1);
+    PT_ALLOC(BigList, Idx, M / 33 + 2);
+    PT_ALLOC(GBits, uint32_t, (KS + 31) / 32 + 1);
+    PT_ALLOC(GPre, Idx, (KS + 31) / 32 + 1);
     fill<uint32_t, BLOCK>(GrpCnt, M + 2, 0u);
     fill<uint32_t, BLOCK>(GrpCur, M + 2, 0u);
     __syncthreads();
@@ -457,7 +467,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         for (uint32_t base = 0; base < M + 1; base += BLOCK) {
             uint32_t q = base + tid, total;
             uint32_t ex = block_scan_excl<BLOCK>(q < M + 1 ? GrpCnt[q] : 0u, c, total);
-            if (q < M + 1) GrpOff[q] = (Idx)(carry + ex);
+            if (q < M + 1) { GrpOff[q] = (Idx)(carry + ex); if (GrpCnt[q] > 32u) BigList[atomicAdd(&c.misc[3], 1u)] = (Idx)q; }
             carry += total;
         }
     }
@@ -467,12 +477,45 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         Unsorted[(uint32_t)GrpOff[q] + atomicAdd(&GrpCur[q], 1u)] = (Idx)r;
     }
     __syncthreads();
+    constexpr uint32_t kBigGroup = 32;                 // larger sibling groups are ranked with a key-space bitmap, not by counting
     for (uint32_t r = tid; r < M; r += BLOCK) {
         uint32_t q = Prun[r], cnt = GrpCnt[q], off = GrpOff[q];
+        if (cnt > kBigGroup) continue;
         uint32_t rank = 0;
         if (cnt > 1) { uint32_t kr = Key[r]; for (uint32_t s = 0; s < cnt; s++) rank += Key[Unsorted[off + s]] > kr ? 1u : 0u; }
         Sorted[off + rank] = (Idx)r;
         SPos[r] = (Idx)(off + rank);
+    }
+    const uint32_t nBig = c.misc[3];
+    if (nBig) {
+        // rank inside a big group = number of members with a larger opId key = members' bits above mine in a bitmap over
+        // the key space (unique keys: a counting sort).  One group at a time, all threads cooperate.
+        const uint32_t KWg = (KS + 31) / 32;
+        for (uint32_t g = 0; g < nBig; g++) {
+            const uint32_t q = BigList[g], cnt = GrpCnt[q], off = GrpOff[q];
+            fill<uint32_t, BLOCK>(GBits, KWg + 1, 0u);
+            __syncthreads();
+            for (uint32_t s2 = tid; s2 < cnt; s2 += BLOCK) { const uint32_t k = Key[Unsorted[off + s2]]; atomicOr(&GBits[k >> 5], 1u << (k & 31)); }
+            __syncthreads();
+            {
+                uint32_t carry = 0;
+                for (uint32_t base = 0; base < KWg; base += BLOCK) {
+                    uint32_t w = base + tid, total;
+                    uint32_t ex = block_scan_excl<BLOCK>(w < KWg ? __popc(GBits[w]) : 0u, c, total);
+                    if (w < KWg) GPre[w] = (Idx)(carry + ex);
+                    carry += total;
+                }
+            }
+            __syncthreads();
+            for (uint32_t s2 = tid; s2 < cnt; s2 += BLOCK) {
+                const uint32_t r = Unsorted[off + s2], k = Key[r];
+                const uint32_t below = (uint32_t)GPre[k >> 5] + __popc(GBits[k >> 5] & ((1u << (k & 31)) - 1u));
+                const uint32_t rank = cnt - 1u - below;          // members with a larger key come first
+                Sorted[off + rank] = (Idx)r;
+                SPos[r] = (Idx)(off + rank);
+            }
+            __syncthreads();
+        }
     }
     __syncthreads();
 
