@@ -189,6 +189,10 @@ int pt_batch_merge(pt_batch*);
 /* Block until the handle's stream is idle. */
 int pt_batch_sync(pt_batch*);
 
+/* Enqueue the device -> host copies of the result arrays without waiting (pinned destinations); a following
+ * pt_batch_download only waits.  Lets a caller overlap this handle's download with other handles' work. */
+int pt_batch_download_begin(pt_batch*);
+
 /* Copy results device -> host (pinned) and return a view. Synchronises the stream. */
 int pt_batch_download(pt_batch*, pt_spans_view* out);
 

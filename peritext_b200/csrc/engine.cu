@@ -119,6 +119,8 @@ struct pt_batch {
     uint64_t launches = 0;
     cudaGraphExec_t graph_exec = nullptr;   // the merge sequence of the current batch, captured once
     bool graph_ok = false, graph_tried = false;
+    uint32_t merges_since_upload = 0;
+    bool dl_begun = false;
     uint32_t kernels_per_merge = 0;
     uint64_t pool_used_host = 0;
 };
@@ -297,7 +299,7 @@ static int upload_common(pt_batch* b, const pt_packed_ops* ops, bool adopt) {
     PT_CUDA(cudaSetDevice(b->device));
     b->have_batch = false; b->merged = false;
     if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
-    b->graph_ok = false; b->graph_tried = false;
+    b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0; b->dl_begun = false;
     int rc = plan_batch(b, ops);
     if (rc) return rc;
     if ((rc = alloc_and_upload_plan(b))) return rc;
@@ -356,7 +358,7 @@ int pt_batch_merge(pt_batch* b) {
     PT_CUDA(cudaSetDevice(b->device));
     // The launch sequence of a batch is fixed: capture it once into a CUDA graph (not possible on the legacy default
     // stream, where the launches are simply enqueued directly).
-    if (!b->graph_tried) {
+    if (!b->graph_tried && b->merges_since_upload >= 1) {   // a batch merged more than once: replay its launch sequence as a graph
         b->graph_tried = true;
         const char* eg = getenv("PT_GRAPH");
         if (b->stream != nullptr && !(eg && atoi(eg) == 0)) {
@@ -383,7 +385,7 @@ int pt_batch_merge(pt_batch* b) {
         if (rc) return rc;
     }
     PT_CUDA(cudaEventRecord(b->ev1, b->stream));
-    b->merged = true;
+    b->merged = true; b->merges_since_upload++; b->dl_begun = false;
     return PT_OK;
 }
 
@@ -413,8 +415,10 @@ int pt_batch_download_results(pt_batch* b, pt_log_result* out, uint32_t n_logs) 
     return PT_OK;
 }
 
-int pt_batch_download(pt_batch* b, pt_spans_view* out) {
-    if (!b || !out) return PT_ERR_INVALID;
+// Enqueue the device -> host copies of every result array (asynchronous, pinned destinations); pt_batch_download then
+// only waits.  Lets a caller overlap one handle's download with another handle's upload / merge.
+int pt_batch_download_begin(pt_batch* b) {
+    if (!b) return PT_ERR_INVALID;
     if (!b->merged) { g_last_error = "download before merge"; return PT_ERR_STATE; }
     int rc;
     const size_t n = b->n_logs;
@@ -426,12 +430,21 @@ int pt_batch_download(pt_batch* b, pt_spans_view* out) {
     if (n) PT_CUDA(cudaMemcpyAsync(b->h_results.p, b->d_results.p, n * sizeof(pt_log_result), cudaMemcpyDeviceToHost, b->stream));
     if (b->n_text) PT_CUDA(cudaMemcpyAsync(b->h_text.p, b->d_text.p, b->n_text * 4, cudaMemcpyDeviceToHost, b->stream));
     if (b->n_span) PT_CUDA(cudaMemcpyAsync(b->h_spans.p, b->d_spans.p, b->n_span * sizeof(pt_span), cudaMemcpyDeviceToHost, b->stream));
-    const bool want_seq = (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) != 0;
-    if (want_seq) {
+    if (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) {
         if ((rc = b->h_seq.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
         if (b->n_text) PT_CUDA(cudaMemcpyAsync(b->h_seq.p, b->d_seq.p, b->n_text * 4, cudaMemcpyDeviceToHost, b->stream));
     }
+    b->dl_begun = true;
+    return PT_OK;
+}
+
+int pt_batch_download(pt_batch* b, pt_spans_view* out) {
+    if (!b || !out) return PT_ERR_INVALID;
+    if (!b->merged) { g_last_error = "download before merge"; return PT_ERR_STATE; }
+    int rc;
+    if (!b->dl_begun && (rc = pt_batch_download_begin(b))) return rc;
     PT_CUDA(cudaStreamSynchronize(b->stream));
+    const bool want_seq = (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) != 0;
     uint64_t used = *(unsigned long long*)b->h_misc.p;
     if (used > b->pool_cap) used = b->pool_cap;
     b->pool_used_host = used;

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libperitext_b200.so")
 _lib = None
 
 EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_adopt_device", "pt_batch_merge", "pt_batch_sync",
-           "pt_batch_download", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count", "pt_batch_stats",
+           "pt_batch_download", "pt_batch_download_begin", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count", "pt_batch_stats",
            "pt_batch_last_merge_ms", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
 
 
@@ -59,6 +59,7 @@ def load_library() -> ctypes.CDLL:
     L.pt_batch_merge.argtypes = [vp]
     L.pt_batch_sync.argtypes = [vp]
     L.pt_batch_download.argtypes = [vp, vp]
+    L.pt_batch_download_begin.argtypes = [vp]
     L.pt_batch_download_results.argtypes = [vp, vp, u32]
     L.pt_batch_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u32)]
     L.pt_batch_launch_count.argtypes = [vp]; L.pt_batch_launch_count.restype = u64
@@ -137,6 +138,9 @@ class BatchEngine:
         _check(self._L.pt_batch_download_results(self._h, out.ctypes.data, self.n_logs), "pt_batch_download_results")
         return out
 
+    def download_begin(self):
+        _check(self._L.pt_batch_download_begin(self._h), "pt_batch_download_begin")
+
     def download(self, copy: bool = True) -> MergedBatch:
         v = _SpansView()
         _check(self._L.pt_batch_download(self._h, ctypes.byref(v)), "pt_batch_download")
@@ -177,3 +181,33 @@ class BatchEngine:
             self.close()
         except Exception:
             pass
+
+
+class PipelinedEngine:
+    """Host <-> device pipelining for one big batch: the batch is cut into `chunks` runs of logs, each with its own
+    engine handle and CUDA stream, so chunk k+1's upload overlaps chunk k's merge and chunk k-1's download (separate
+    copy engines).  Inputs should live in pinned host memory (otherwise the uploads synchronise)."""
+
+    def __init__(self, device: int = 0, chunks: int = 4, streams=None):
+        self.chunks = chunks
+        self._streams = streams
+        if streams is None:
+            import torch
+            self._streams = [torch.cuda.Stream(device=device) for _ in range(chunks)]
+        self.engines = [BatchEngine(device, stream=s.cuda_stream) for s in self._streams]
+
+    def run(self, batch: PackedBatch, copy: bool = False) -> list[MergedBatch]:
+        n = batch.n_logs
+        # cut by records, not by log count, so the chunks carry similar work
+        w = np.cumsum(batch.desc["n_insdel"].astype(np.int64) + 2 * batch.desc["n_mark"].astype(np.int64))
+        cuts = [0] + [int(np.searchsorted(w, w[-1] * (k + 1) / self.chunks, side="left")) + 1 for k in range(self.chunks - 1)] + [n] if n else [0, 0]
+        cuts = sorted(set(min(max(c, 0), n) for c in cuts))
+        subs = [batch.slice_logs(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
+        used = self.engines[: len(subs)]
+        for e, sb in zip(used, subs):
+            e.upload(sb); e.merge(); e.download_begin()
+        return [e.download(copy=copy) for e in used]
+
+    def close(self):
+        for e in self.engines:
+            e.close()

@@ -87,6 +87,17 @@ class PackedBatch:
         return (self.insdel[int(d["insdel_off"]): int(d["insdel_off"]) + int(d["n_insdel"])],
                 self.marks[int(d["mark_off"]): int(d["mark_off"]) + int(d["n_mark"])])
 
+    def slice_logs(self, a: int, b: int) -> "PackedBatch":
+        """Logs [a, b) as VIEWS of this batch's arrays (no copy: pinned host memory stays pinned); offsets re-based."""
+        d = self.desc[a:b].copy()
+        if len(d) == 0:
+            return PackedBatch(d, self.insdel[:0], self.marks[:0], self.values, self.link_attrs, self.comment_ids, self.other_attrs, dict(self.meta))
+        i0, m0 = int(d[0]["insdel_off"]), int(d[0]["mark_off"])
+        i1 = int(d[-1]["insdel_off"]) + int(d[-1]["n_insdel"]); m1 = int(d[-1]["mark_off"]) + int(d[-1]["n_mark"])
+        d["insdel_off"] -= i0; d["mark_off"] -= m0
+        return PackedBatch(d, self.insdel[i0:i1], self.marks[m0:m1], self.values, self.link_attrs, self.comment_ids, self.other_attrs,
+                           dict(self.meta), self.log_actors[a:b] if self.log_actors else [])
+
     def select(self, idx: Sequence[int]) -> "PackedBatch":
         """Sub-batch with the given logs (re-based offsets); pools are shared."""
         idx = list(idx)

@@ -146,3 +146,20 @@ def test_cuda_graph_path_on_a_user_stream():
         ref, _ = replay_packed(batch, threads=2)
         assert_batch_equal(batch, got, ref)
     eng.close()
+
+
+def test_pipelined_engine_equals_single_handle():
+    from peritext_b200 import workload
+    from peritext_b200.engine import BatchEngine, PipelinedEngine
+    batch = workload.generate("c3", n_docs=24, ops_per_doc=2000)
+    eng = BatchEngine(0)
+    whole = eng.run(batch)
+    pipe = PipelinedEngine(0, chunks=4)
+    parts = pipe.run(batch, copy=True)
+    assert sum(p.results.shape[0] for p in parts) == batch.n_logs
+    k = 0
+    for p in parts:
+        for i in range(p.results.shape[0]):
+            assert p.canonical(i) == whole.canonical(k), k
+            k += 1
+    pipe.close(); eng.close()
