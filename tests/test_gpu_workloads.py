@@ -77,3 +77,30 @@ def test_merge_is_idempotent_and_order_of_logs_irrelevant(engine):
     c = engine.run(batch.select(perm))
     for k, i in enumerate(perm):
         assert c.canonical(k) == a.canonical(i)
+
+
+def test_empty_batch_and_empty_logs(engine):
+    import numpy as np
+    from peritext_b200.packing import DESC_DT, INSDEL_DT, MARK_DT, PackedBatch
+    empty = PackedBatch(np.zeros(0, DESC_DT), np.zeros(0, INSDEL_DT), np.zeros(0, MARK_DT))
+    got = engine.run(empty)
+    assert got.results.shape[0] == 0
+    # logs without any record between real ones
+    batch = workload.generate("c3", n_docs=2, ops_per_doc=300)
+    d = np.zeros(batch.n_logs + 2, DESC_DT)
+    d[0] = (0, 0, 0, 0, 1, 1)
+    d[1:-1] = batch.desc
+    d[-1] = (len(batch.insdel), len(batch.marks), 0, 0, 1, 1)
+    mixed = PackedBatch(d, batch.insdel, batch.marks, meta=dict(batch.meta))
+    got = engine.run(mixed)
+    ref, _ = replay_packed(mixed)
+    for i in range(mixed.n_logs):
+        assert got.canonical(i) == ref.canonical(i), i
+    assert got.results[0]["n_spans"] == 0 and got.results[-1]["n_visible"] == 0
+
+
+@pytest.mark.parametrize("ops", [31900, 32100])
+def test_index_width_boundary(engine, ops):
+    # just below / above the u16 -> u32 index switch (32000 records per log)
+    batch = workload.generate("c2", n_docs=1, ops_per_doc=ops)
+    full_compare(engine, batch, threads=2)
