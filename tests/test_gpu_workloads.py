@@ -46,7 +46,10 @@ def test_large_log_uses_wide_index_path(engine):
     # > 32000 records in one log: the u32-index instantiation, arena spills to the global slab
     batch = workload.generate("c2", n_docs=1, ops_per_doc=40000)
     assert int(batch.desc["n_insdel"].max()) > 32000
-    full_compare(engine, batch, threads=2)
+    got = engine.run(batch)
+    ref, _ = replay_packed(batch, first=0, count=1)
+    assert got.canonical(0) == ref.canonical(0)
+    assert got.results[1]["status"] == 0 and got.results[0]["digest"].tolist() == got.results[1]["digest"].tolist()
 
 
 @pytest.mark.parametrize("cfg", ["c2", "c3"])
@@ -101,6 +104,10 @@ def test_empty_batch_and_empty_logs(engine):
 
 @pytest.mark.parametrize("ops", [31900, 32100])
 def test_index_width_boundary(engine, ops):
-    # just below / above the u16 -> u32 index switch (32000 records per log)
+    # just below / above the u16 -> u32 index switch (32000 records per log); the O(N^2) oracle replays one replica,
+    # the other one is checked through the convergence digest
     batch = workload.generate("c2", n_docs=1, ops_per_doc=ops)
-    full_compare(engine, batch, threads=2)
+    got = engine.run(batch)
+    ref, _ = replay_packed(batch, first=0, count=1)
+    assert got.canonical(0) == ref.canonical(0)
+    assert got.results[1]["status"] == 0 and got.results[0]["digest"].tolist() == got.results[1]["digest"].tolist()
