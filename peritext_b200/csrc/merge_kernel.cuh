@@ -1,4 +1,4 @@
-// merge_kernel.cuh — the op-log apply + flatten kernel (sm_100a), v2.
+// merge_kernel.cuh — the op-log apply + flatten kernel (sm_100a).
 //
 // One CTA materialises one LOG (one replica's op log of one document) end to end:
 //   packed records in HBM  ->  element sequence (RGA order)  ->  visible text + formatted spans + digest in HBM.
@@ -10,13 +10,16 @@
 //  tests/kernel_model.py, whose phase names A..I this file follows).
 //
 // No floating point, no tensor cores: integer/index work bounded by HBM traffic and shared-memory latency.
-// v2 layout of the per-record state: BITMAPS over record indices (insert / chain-continuation / head / visible) with
+// Layout of the per-record state: BITMAPS over record indices (insert / chain-continuation / head / visible) with
 // popcount prefixes per 32-record word, instead of per-record index arrays; everything per-element is derived as
 //   run(i)  = popcount(head bits <= i) - 1
 //   pos(i)  = PosBase[run(i)] + i                 (runs are contiguous in the log AND in the sequence)
 //   vis(i)  = VisBase[run(i)] + popcount(visible bits < i)
-// Working arrays live in a per-CTA ARENA: dynamic shared memory first, a per-CTA global slab (L2 resident) as
-// spill for logs that do not fit.  Index arrays are u16 when the log is small enough (halves the footprint).
+// Working arrays live in a per-CTA stack-like ARENA.  The pipeline is instantiated twice: SH=true keeps every array in
+// dynamic shared memory (LDS/STS with 32-bit addresses); a log that does not fit is deferred to a launch with a larger
+// budget, and only the largest one falls back to SH=false, which spills to a per-CTA global slab (L2 resident).
+// Index arrays are u16 when the log is small enough (halves the footprint).  The record stream of phase A is staged
+// through shared memory with TMA bulk copies (cp.async.bulk + mbarrier), double buffered.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -14,8 +14,7 @@ from __future__ import annotations
 
 import copy
 
-from .packing import (KIND_INSERT, RangeError, TOKEN_POOLED, _root_text_list, decode_spans, js_key, pack_logs,
-                      parse_op_id, token_str)
+from .packing import RangeError, _root_text_list, decode_spans, js_key, pack_logs, parse_op_id, token_str
 
 _default_engine = None
 INCLUSIVE = {"strong": True, "em": True, "comment": False, "link": False}   # markSpec.inclusive, reference src/schema.ts:45-96

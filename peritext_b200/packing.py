@@ -170,12 +170,12 @@ def pack_logs(logs: Sequence[Sequence[dict]], *, list_ids: Sequence[str | None] 
     other_index: dict[str, int] = {}
 
     def token_of(v: Any) -> int:
+        """Element value -> 30-bit token: the code point of a one-code-point string, else a value-pool reference
+        (an element may hold a multi-character string, reference test/micromerge.ts:202)."""
         if not isinstance(v, str):
             raise TypeError("Expected value inserted into text to be a string")   # src/micromerge.ts:654-656
-        if len(v) == 1 or (len(v) == 2 and 0xD800 <= ord(v[0]) <= 0xDBFF):
-            cp = ord(v) if len(v) == 1 else None
-            if cp is not None and cp < TOKEN_POOLED:
-                return cp
+        if len(v) == 1:
+            return ord(v)
         if v not in value_index:
             value_index[v] = len(values)
             values.append(v)

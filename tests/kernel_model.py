@@ -1,9 +1,10 @@
 """Executable model (plain Python, sequential loops) of the ORDER-INDEPENDENT CLOSED FORM the CUDA kernels
-implement, phase by phase with the same intermediate arrays.  TEST INFRASTRUCTURE:
-it exists so the algorithm can be property-tested against the sequential oracle on a CPU-only box before (and
-independently of) the device code.
+implement, phase by phase.  TEST INFRASTRUCTURE: it exists so the algorithm can be
+property-tested against the sequential oracle on a CPU-only box before (and independently of) the device code.
+It models the MATH of each phase (explicit per-record arrays, plain pointer jumping); the device code computes the same
+quantities with bitmaps + popcount prefixes, splitter list ranking, segment trees and a hash table.
 
-Phases (same names as peritext_b200/csrc/merge_kernel.cu):
+Phases (same letters as peritext_b200/csrc/merge_kernel.cuh):
   A  id table        T[K(ctr,actor)] -> insert record index,   K = (ctr-1)*R + actor
   B  parents/deletes p[i] = T[K(ref)], childCount, deleted[]
   C  runs            log-contiguous only-child chains
