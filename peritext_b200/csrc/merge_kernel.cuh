@@ -270,23 +270,38 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         if (lane == 0 && ccnt) atomicAdd(&c.misc[2], ccnt);
     }
 
-    // ---- A: id table + insert / chain-continuation bitmaps (first and only HBM read of the records) ------------
-    // cand(i): record i is an insert whose reference element is the insert at record i-1 (a typing chain link)
+    // ---- A+B, fused per chunk of records (the only pass over the records before the text pass) ---------------------------
+    // A: id table T[K(opId)] and the insert / chain-link bitmaps.  cand(i): record i is an insert whose reference element
+    //    is the insert at record i-1 (a typing chain link) — decided by comparing with the left neighbour, no lookup.
+    // B: after the chunk's ids are in the table: parents of chain heads (-> "has another child" flags) and deletes
+    //    (-> tombstones), one code path for both.  A referenced element must arrive EARLIER in the log, as in the
+    //    reference, where applyOp throws "List element not found" otherwise (src/micromerge.ts:752).
     {
         const uint4 zero4 = make_uint4(0, 0, 0, 0xC0000000u);     // kind 3: neither insert nor delete
-        auto stepA = [&](uint32_t i, const uint4 r, const uint4 rp) {
+        auto stepA = [&](uint32_t i, const uint4 r, const uint4 rp) -> bool {   // returns: record needs a table lookup in B
             const uint32_t ctr = r.x, actor = r.z & 0xFFFFu, ref_ctr = r.y, ref_actor = r.z >> 16, kind = r.w >> 30;
-            bool isIns = false;
+            bool isIns = false, valid = false;
             if (i < n) {
                 if (kind > 1u) fail(PT_LOG_BAD_KIND);
                 else if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
-                else if (kind == PT_KIND_INSERT) { isIns = true; T[keyOf(ctr, actor)] = (Idx)i; }
+                else { valid = true; if (kind == PT_KIND_INSERT) { isIns = true; T[keyOf(ctr, actor)] = (Idx)i; } }
             }
             // reference element == the insert at record i-1 ?
             bool cand = isIns && ref_ctr != 0 && ref_ctr == rp.x && ref_actor == (rp.z & 0xFFFFu) && (rp.w >> 30) == PT_KIND_INSERT;
             if (cand && keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); cand = false; }
             const uint32_t insW = __ballot_sync(0xffffffffu, isIns), candW = __ballot_sync(0xffffffffu, cand);
             if (lane == 0 && i < n) { InsBits[i >> 5] = insW; HeadBits[i >> 5] = candW; }
+            return valid && !cand;
+        };
+        auto stepB = [&](uint32_t i, bool live, const uint4 r) {
+            if (!live) return;
+            const uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16;
+            const bool isIns = (r.w >> 30) == PT_KIND_INSERT;
+            if (ref_ctr == 0) { if (!isIns) fail(PT_LOG_ELEM_NOT_FOUND); return; }        // insert: child of HEAD
+            const Idx j = badId(ref_ctr, ref_actor) ? NONE : T[keyOf(ref_ctr, ref_actor)];
+            if (j == NONE || (uint32_t)j >= i) { fail(PT_LOG_ELEM_NOT_FOUND); return; }   // must have arrived earlier (deterministic)
+            if (isIns && keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); return; }
+            (isIns ? Other : Del)[j] = 1;        // deletes: OR, idempotent (micromerge.ts:689)
         };
         if (SH && P.use_tma) {
             // TMA-staged record stream: chunks of 2*BLOCK records land in a double-buffered shared-memory stage
@@ -311,10 +326,12 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
                 uint4 p0 = zero4, p1 = zero4;
                 if (i0 < n) { if (tid > 0) p0 = st[tid - 1]; else if (i0 > 0) p0 = ld_rec(ins + i0 - 1); }
                 if (i1 < n) p1 = st[BLOCK + tid - 1];
-                stepA(i0, r0, p0);
-                stepA(i1, r1, p1);
-                __syncthreads();                                   // everyone is done with buffer b
+                const bool l0 = stepA(i0, r0, p0);
+                const bool l1 = stepA(i1, r1, p1);
+                __syncthreads();                                   // the chunk's ids are in T; everyone is done with buffer b
                 if (tid == 0 && k + 2 < nch) { fence_proxy_async(); issue(k + 2); }
+                stepB(i0, l0, r0);
+                stepB(i1, l1, r1);
             }
             A.sm_used = stage_mark;                                // release the stage
         } else
@@ -323,32 +340,9 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             const uint4 r0 = i0 < n ? ld_rec(ins + i0) : zero4, r1 = i1 < n ? ld_rec(ins + i1) : zero4;
             // the left neighbours (same cache lines, L1 hits)
             const uint4 p0 = (i0 > 0 && i0 < n) ? ld_rec(ins + i0 - 1) : zero4, p1 = i1 < n ? ld_rec(ins + i1 - 1) : zero4;
-            stepA(i0, r0, p0);
-            stepA(i1, r1, p1);
-        }
-    }
-    __syncthreads();
-    if (c.status) { bail(); return 0; }
-
-    // ---- B: parents of chain heads (-> "has another child" flags), deletes (-> tombstones): one code path for both ----
-    {
-        auto stepB = [&](uint32_t i, bool live, const uint4 r) {
-            if (!live) return;
-            const uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16;
-            const bool isIns = (r.w >> 30) == PT_KIND_INSERT;
-            if (ref_ctr == 0) { if (!isIns) fail(PT_LOG_ELEM_NOT_FOUND); return; }        // insert: child of HEAD
-            const Idx j = badId(ref_ctr, ref_actor) ? NONE : T[keyOf(ref_ctr, ref_actor)];
-            if (j == NONE) { fail(PT_LOG_ELEM_NOT_FOUND); return; }
-            if (isIns && keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); return; }
-            (isIns ? Other : Del)[j] = 1;        // deletes: OR, idempotent (micromerge.ts:689)
-        };
-        for (uint32_t base = 0; base < n; base += 2 * BLOCK) {
-            const uint32_t i0 = base + tid, i1 = i0 + BLOCK;
-            // chain links need no lookup: their parent is record i-1
-            const bool l0 = i0 < n && !((HeadBits[i0 >> 5] >> (i0 & 31)) & 1u), l1 = i1 < n && !((HeadBits[i1 >> 5] >> (i1 & 31)) & 1u);
-            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-            if (l0) r0 = ld_rec(ins + i0);
-            if (l1) r1 = ld_rec(ins + i1);
+            const bool l0 = stepA(i0, r0, p0);
+            const bool l1 = stepA(i1, r1, p1);
+            __syncthreads();                                       // the trip's ids are in T
             stepB(i0, l0, r0);
             stepB(i1, l1, r1);
         }
