@@ -23,7 +23,7 @@ for k in keys:
         print(f"| {k} | {m[k]} |", file=out)
 kernel_src = open("peritext_b200/csrc/merge_kernel.cuh").read().split("\n")
 marks = [("helpers (scan/arena/fill/digest)", 1)]
-for name, pat in [("setup", "__device__ int merge_one_log"), ("A id table + chain bits (HBM read)", "// ---- A:"), ("B heads' parents, deletes", "// ---- B:"),
+for name, pat in [("setup", "__device__ int merge_one_log"), ("A+B id table, chain bits, parents, deletes (TMA-staged HBM read)", "// ---- A+B"),
                   ("C runs (bit-parallel)", "// ---- C:"), ("D run tree, sibling order", "// ---- D:"), ("E Euler ranking", "// ---- E:"),
                   ("F text out", "// ---- F:"), ("G marks: rank, intervals, segments", "// ---- G:"), ("G3 LWW trees", "// G3:"),
                   ("H comments", "// ---- H:"), ("I spans", "// ---- I:"), ("I comment lists + span records", "// comment lists per span"),
