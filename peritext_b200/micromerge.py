@@ -103,6 +103,7 @@ class Micromerge:
             raise JsError("engine was created without emit_sequence; change()/cursors need the element sequence")
         ins, _ = batch.log_slice(0)
         actors = batch.log_actors[0]
+        cmap = batch.log_counters[0] if batch.log_counters else None     # dense counter rank -> original counter
         after_defined = set()      # elements whose markOpsAfter slot is defined: some applied op ends `after` them (peritext.ts:239-241)
         for ch in self._applied:
             for op in ch["ops"]:
@@ -111,7 +112,8 @@ class Micromerge:
         mirror = []
         for e in merged.sequence(0):
             r = ins[int(e) & 0x7FFFFFFF]
-            eid = f"{int(r['ctr'])}@{actors[int(r['actor'])]}"
+            ctr = int(r["ctr"]) if cmap is None else int(cmap[int(r["ctr"])])
+            eid = f"{ctr}@{actors[int(r['actor'])]}"
             tok = int(r["payload"]) & 0x3FFFFFFF
             mirror.append([eid, bool(int(e) >> 31), eid in after_defined, token_str(tok, batch.values)])
         self._mirror, self._mirror_list = mirror, lid

@@ -73,6 +73,7 @@ class PackedBatch:
     other_attrs: list[Any] = field(default_factory=list)   # strong/em attrs (normally none)
     meta: dict = field(default_factory=dict)
     log_actors: list[list[str]] = field(default_factory=list)   # per log: actor rank -> actorId
+    log_counters: list = field(default_factory=list)            # per log: None, or dense counter rank -> original counter
 
     @property
     def n_logs(self) -> int:
@@ -96,7 +97,8 @@ class PackedBatch:
         i1 = int(d[-1]["insdel_off"]) + int(d[-1]["n_insdel"]); m1 = int(d[-1]["mark_off"]) + int(d[-1]["n_mark"])
         d["insdel_off"] -= i0; d["mark_off"] -= m0
         return PackedBatch(d, self.insdel[i0:i1], self.marks[m0:m1], self.values, self.link_attrs, self.comment_ids, self.other_attrs,
-                           dict(self.meta), self.log_actors[a:b] if self.log_actors else [])
+                           dict(self.meta), self.log_actors[a:b] if self.log_actors else [],
+                           self.log_counters[a:b] if self.log_counters else [])
 
     def select(self, idx: Sequence[int]) -> "PackedBatch":
         """Sub-batch with the given logs (re-based offsets); pools are shared."""
@@ -255,14 +257,29 @@ def pack_logs(logs: Sequence[Sequence[dict]], *, list_ids: Sequence[str | None] 
     insdel = np.zeros(n_ins, INSDEL_DT)
     marks = np.zeros(n_mk, MARK_DT)
     io = mo = 0
+    counters: list = []      # per log: None, or dense counter rank -> original counter
     for li, b in enumerate(builders):
         ranked = sorted(b.actors, key=js_key)
         rank = {a: i for i, a in enumerate(ranked)}
         if len(ranked) > 0xFFFF:
             raise ValueError("more than 65535 actors in one log")
-        desc[li] = (io, mo, len(b.insdel), len(b.marks), max(1, len(ranked)), b.max_ctr)
+        # Sparse counters (a peer may choose any startOp, reference src/micromerge.ts:511): the engine's id table is
+        # direct-addressed by (ctr, actor), so counters far beyond the op count are re-ranked densely.  Only the ORDER
+        # of counters matters to compareOpIds, and the dense rank preserves it.
+        dense = None
+        if b.max_ctr > 2 * (len(b.insdel) + len(b.marks)) + 16:
+            used = {c for (c, _a, rc, _ra, _k, _t) in b.insdel for c in (c, rc)} | {c for mk_ in b.marks for c in (mk_[0], mk_[4][1], mk_[5][1])}
+            used.discard(0)
+            order = sorted(used)
+            dense = {c: i + 1 for i, c in enumerate(order)}
+            dense[0] = 0
+            counters.append(np.array([0] + order, dtype=np.uint64))
+        else:
+            counters.append(None)
+        dc = (lambda c: dense[c]) if dense is not None else (lambda c: c)
+        desc[li] = (io, mo, len(b.insdel), len(b.marks), max(1, len(ranked)), dc(b.max_ctr) if dense is not None else b.max_ctr)
         for k, (ctr, actor, rc, ra, kind, tok) in enumerate(b.insdel):
-            insdel[io + k] = (ctr, rc, rank[actor], rank[ra] if ra is not None else 0, (kind << 30) | tok)
+            insdel[io + k] = (dc(ctr), dc(rc), rank[actor], rank[ra] if ra is not None else 0, (kind << 30) | tok)
         for k, (ctr, actor, add, mt, sb, eb, attr_ref, arrival) in enumerate(b.marks):
             if attr_ref is None:
                 attr = ATTR_NONE
@@ -273,12 +290,12 @@ def pack_logs(logs: Sequence[Sequence[dict]], *, list_ids: Sequence[str | None] 
             else:
                 attr = ATTR_NONE  # non-default strong/em attrs are not representable on the device path
                 raise NotImplementedError("strong/em marks with custom attrs")
-            marks[mo + k] = (ctr, rank[actor], (0 if add else 1) | (mt << 1), sb[0] | (eb[0] << 2),
-                             sb[1], eb[1], rank[sb[2]] if sb[2] is not None else 0,
+            marks[mo + k] = (dc(ctr), rank[actor], (0 if add else 1) | (mt << 1), sb[0] | (eb[0] << 2),
+                             dc(sb[1]), dc(eb[1]), rank[sb[2]] if sb[2] is not None else 0,
                              rank[eb[2]] if eb[2] is not None else 0, attr, arrival, 0)
         io += len(b.insdel); mo += len(b.marks)
     return PackedBatch(desc, insdel, marks, values, link_attrs, [comment_objs[c] for c in comment_sorted], other_attrs,
-                       log_actors=[sorted(b.actors, key=js_key) for b in builders])
+                       log_actors=[sorted(b.actors, key=js_key) for b in builders], log_counters=counters)
 
 
 # ------------------------------------------------------------------------------------------------------------------

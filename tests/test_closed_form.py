@@ -125,3 +125,21 @@ def test_error_statuses():
     ref, _ = replay_packed(bad)
     assert ref.results[0]["status"] == 1
     assert kernel_model.merge_batch(bad).results[0]["status"] == 1
+
+
+def test_sparse_counters_are_reranked_densely():
+    """A peer may pick any startOp (reference src/micromerge.ts:511 only takes the max): counters far beyond the op count
+    are re-ranked by the packer; order — all that compareOpIds looks at — is preserved."""
+    docs, _, init = generateDocs(Micromerge, "abc", 2)
+    d1, d2 = docs
+    big = {"actor": "doc2", "seq": 1, "deps": {"doc1": 1}, "startOp": 5_000_000, "ops": [
+        {"opId": "5000000@doc2", "action": "set", "obj": "1@doc1", "elemId": "2@doc1", "insert": True, "value": "X"},
+        {"opId": "5000001@doc2", "action": "set", "obj": "1@doc1", "elemId": "5000000@doc2", "insert": True, "value": "Y"},
+        {"opId": "5000002@doc2", "action": "addMark", "obj": "1@doc1", "start": {"type": "before", "elemId": "5000000@doc2"},
+         "end": {"type": "after", "elemId": "3@doc1"}, "markType": "link", "attrs": {"url": "u"}}]}
+    d1.applyChange(big)
+    c = d1.change([{"path": ["text"], "action": "insert", "index": 1, "values": ["Z"]}])["change"]   # 5000003@doc1, after 'a'
+    logs = [[init, big, c]]
+    b = pack_logs(logs)
+    assert int(b.desc[0]["max_ctr"]) < 20 and b.log_counters[0] is not None
+    check_equal(logs, [d1.getTextWithFormatting()])
