@@ -87,6 +87,35 @@ typedef struct pt_log_desc {
     uint32_t max_ctr;    /* every ctr in the log is in [1, max_ctr]                                */
 } pt_log_desc;
 
+/* ------------------------------------------------------------------------------------------------
+ * Run-compressed wire format (optional, for the host -> device leg).  The ops of one Change are
+ * consecutive (`opId = ++maxOp`, src/micromerge.ts:487) and a typed run chains every insert to the
+ * previous one (`elemId = result`, :351-359), so the ins/del stream compresses to RUNS:
+ *   insert run: `count` inserts with opIds (ctr0 + k, actor); the first references (ref_ctr, ref_actor),
+ *               each following one references its predecessor; values = `count` tokens of the token stream
+ *   delete run: `count` deletes with opIds (ctr0 + k, actor) of the elements (ref_ctr + k, ref_actor)
+ * pt_batch_upload_runs expands runs to pt_insdel_rec on the device; results are identical.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_run_rec {
+    uint32_t ctr0;
+    uint32_t ref_ctr;
+    uint16_t actor;
+    uint16_t ref_actor;
+    uint32_t kind_count; /* bits31:30 kind (PT_KIND_*), bits29:0 count (>= 1) */
+} pt_run_rec;
+
+typedef struct pt_packed_runs {
+    uint32_t n_logs;
+    const pt_log_desc* logs;      /* [n_logs] — the EXPANDED layout (insdel_off / n_insdel count records)      */
+    const uint64_t* run_off;      /* [n_logs + 1] first run of each log                                         */
+    const uint64_t* tok_off;      /* [n_logs + 1] first insert token of each log                                */
+    const pt_run_rec* runs;       /* [run_off[n_logs]]                                                          */
+    const uint32_t* tokens;       /* [tok_off[n_logs]] PT_PAYLOAD_TOKEN values of the inserts, in record order  */
+    const pt_mark_rec* marks;     /* [n_mark_total] (not compressed)                                            */
+    uint64_t n_insdel_total;      /* expanded record count                                                      */
+    uint64_t n_mark_total;
+} pt_packed_runs;
+
 /* A host-side batch of logs (SoA). */
 typedef struct pt_packed_ops {
     uint32_t n_logs;
@@ -177,6 +206,15 @@ int pt_batch_create(int device, const pt_limits* limits, void* cuda_stream, pt_b
  * through engine-owned pinned memory, so the caller may free them on return). Replaces any previous batch.
  * This is the H2D leg of Micromerge.applyChange's input (src/micromerge.ts:499). */
 int pt_batch_upload(pt_batch*, const pt_packed_ops* host_ops);
+
+/* Same as pt_batch_upload for the run-compressed form: copies runs / tokens / marks host -> device and expands the runs
+ * to pt_insdel_rec records on the device (one small kernel).  Typically 2-3x fewer bytes over PCIe. */
+int pt_batch_upload_runs(pt_batch*, const pt_packed_runs* host_runs);
+
+/* Host helper: compress a packed batch into runs.  Call once with runs == NULL / tokens == NULL to get the counts
+ * (*n_runs, *n_tokens), then with buffers of that size; run_off / tok_off need n_logs + 1 entries. */
+int pt_compress_runs(const pt_packed_ops* ops, uint64_t* run_off, uint64_t* tok_off, pt_run_rec* runs, uint32_t* tokens,
+                     uint64_t* n_runs, uint64_t* n_tokens);
 
 /* Adopt a batch that is ALREADY RESIDENT in device memory (pointers are device pointers owned by the
  * caller, e.g. torch tensors); only the descriptors are read on the host. */

@@ -92,6 +92,47 @@ size_t arena_worst_bytes(uint64_t n, uint64_t m, uint64_t KS) {
     return b + 256;
 }
 
+// Expands run-compressed ins/del streams into pt_insdel_rec records (one warp per log, lanes over the runs; a run's
+// records are written by its lane — runs are short, and the expanded array is consumed from L2/HBM by the merge kernel).
+__global__ void expand_runs_kernel(const pt_log_desc* __restrict__ desc, const unsigned long long* __restrict__ run_off,
+                                   const unsigned long long* __restrict__ tok_off, const pt_run_rec* __restrict__ runs,
+                                   const uint32_t* __restrict__ tokens, pt_insdel_rec* __restrict__ out, uint32_t n_logs) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t li = warp; li < n_logs; li += nwarps) {
+        const unsigned long long r0 = run_off[li], r1 = run_off[li + 1];
+        pt_insdel_rec* o = out + desc[li].insdel_off;
+        const uint32_t* tk = tokens + tok_off[li];
+        uint32_t rec_base = 0, tok_base = 0;
+        for (unsigned long long rb = r0; rb < r1; rb += 32) {
+            const unsigned long long ri = rb + lane;
+            uint4 r = make_uint4(0, 0, 0, 0);
+            uint32_t cnt = 0, kind = 0;
+            if (ri < r1) { r = __ldg(reinterpret_cast<const uint4*>(runs + ri)); cnt = r.w & 0x3FFFFFFFu; kind = r.w >> 30; }
+            uint32_t tcnt = kind == PT_KIND_INSERT ? cnt : 0u;
+            // exclusive prefix sums of the record and token counts inside the warp
+            uint32_t pr = cnt, pt = tcnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(0xffffffffu, pr, d), b2 = __shfl_up_sync(0xffffffffu, pt, d); if (lane >= (uint32_t)d) { pr += a; pt += b2; } }
+            const uint32_t tot_r = __shfl_sync(0xffffffffu, pr, 31), tot_t = __shfl_sync(0xffffffffu, pt, 31);
+            uint32_t ro = rec_base + pr - cnt, to = tok_base + pt - tcnt;
+            const uint32_t actor = r.z & 0xFFFFu;
+            for (uint32_t k = 0; k < cnt; k++) {
+                uint4 w;
+                w.x = r.x + k;
+                if (kind == PT_KIND_INSERT) {
+                    w.y = k == 0 ? r.y : r.x + k - 1;
+                    w.z = actor | ((k == 0 ? (r.z >> 16) : actor) << 16);
+                    w.w = (PT_KIND_INSERT << 30) | tk[to + k];
+                } else {
+                    w.y = r.y + k; w.z = r.z; w.w = kind << 30;
+                }
+                reinterpret_cast<uint4*>(o)[ro + k] = w;
+            }
+            rec_base += tot_r; tok_base += tot_t;
+        }
+    }
+}
+
 }  // namespace
 
 struct pt_batch {
@@ -110,6 +151,7 @@ struct pt_batch {
     size_t bin_slab[kNumBins] = {0};
     size_t retry_slab = 0;
     // device
+    DevBuf d_runs, d_tokens, d_run_off, d_tok_off;
     DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_slab, d_retry, d_seq;
     const pt_insdel_rec* dp_insdel = nullptr;
     const pt_mark_rec* dp_marks = nullptr;
@@ -324,6 +366,83 @@ static int upload_common(pt_batch* b, const pt_packed_ops* ops, bool adopt) {
 }
 
 int pt_batch_upload(pt_batch* b, const pt_packed_ops* ops) { return upload_common(b, ops, false); }
+
+int pt_batch_upload_runs(pt_batch* b, const pt_packed_runs* rr) {
+    if (!b || !rr || (rr->n_logs && (!rr->logs || !rr->run_off || !rr->tok_off))) return PT_ERR_INVALID;
+    PT_CUDA(cudaSetDevice(b->device));
+    b->have_batch = false; b->merged = false;
+    if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
+    b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0; b->dl_begun = false;
+    pt_packed_ops ops{rr->n_logs, rr->logs, nullptr, rr->n_insdel_total, nullptr, rr->n_mark_total};
+    int rc = plan_batch(b, &ops);
+    if (rc) return rc;
+    if ((rc = alloc_and_upload_plan(b))) return rc;
+    const size_t nl = rr->n_logs;
+    const uint64_t n_runs = nl ? rr->run_off[nl] : 0, n_tok = nl ? rr->tok_off[nl] : 0;
+    if ((rc = b->d_insdel.reserve(std::max<uint64_t>(1, b->n_insdel) * sizeof(pt_insdel_rec)))) return rc;
+    if ((rc = b->d_marks.reserve(std::max<uint64_t>(1, b->n_mark) * sizeof(pt_mark_rec)))) return rc;
+    if ((rc = b->d_runs.reserve(std::max<uint64_t>(1, n_runs) * sizeof(pt_run_rec)))) return rc;
+    if ((rc = b->d_tokens.reserve(std::max<uint64_t>(1, n_tok) * 4))) return rc;
+    if ((rc = b->d_run_off.reserve((nl + 1) * 8))) return rc;
+    if ((rc = b->d_tok_off.reserve((nl + 1) * 8))) return rc;
+    if (nl) {
+        PT_CUDA(cudaMemcpyAsync(b->d_run_off.p, rr->run_off, (nl + 1) * 8, cudaMemcpyHostToDevice, b->stream));
+        PT_CUDA(cudaMemcpyAsync(b->d_tok_off.p, rr->tok_off, (nl + 1) * 8, cudaMemcpyHostToDevice, b->stream));
+    }
+    if (n_runs) PT_CUDA(cudaMemcpyAsync(b->d_runs.p, rr->runs, n_runs * sizeof(pt_run_rec), cudaMemcpyHostToDevice, b->stream));
+    if (n_tok) PT_CUDA(cudaMemcpyAsync(b->d_tokens.p, rr->tokens, n_tok * 4, cudaMemcpyHostToDevice, b->stream));
+    if (b->n_mark) PT_CUDA(cudaMemcpyAsync(b->d_marks.p, rr->marks, b->n_mark * sizeof(pt_mark_rec), cudaMemcpyHostToDevice, b->stream));
+    if (nl) {
+        const uint32_t threads = 128, warps_needed = (uint32_t)nl;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)warps_needed * 32 + threads - 1) / threads, (uint64_t)b->num_sms * 16);
+        expand_runs_kernel<<<grid, threads, 0, b->stream>>>((const pt_log_desc*)b->d_desc.p, (const unsigned long long*)b->d_run_off.p,
+                                                          (const unsigned long long*)b->d_tok_off.p, (const pt_run_rec*)b->d_runs.p,
+                                                          (const uint32_t*)b->d_tokens.p, (pt_insdel_rec*)b->d_insdel.p, (uint32_t)nl);
+        PT_CUDA(cudaGetLastError());
+        b->launches++;
+    }
+    b->dp_insdel = (const pt_insdel_rec*)b->d_insdel.p; b->dp_marks = (const pt_mark_rec*)b->d_marks.p; b->adopted = false;
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    if (!((n_runs == 0 || pinned(rr->runs)) && (n_tok == 0 || pinned(rr->tokens)) && (b->n_mark == 0 || pinned(rr->marks)) && (nl == 0 || (pinned(rr->run_off) && pinned(rr->tok_off)))))
+        PT_CUDA(cudaStreamSynchronize(b->stream));
+    b->have_batch = true;
+    return PT_OK;
+}
+
+int pt_compress_runs(const pt_packed_ops* ops, uint64_t* run_off, uint64_t* tok_off, pt_run_rec* runs, uint32_t* tokens,
+                     uint64_t* n_runs_out, uint64_t* n_tokens_out) {
+    if (!ops || !run_off || !tok_off) return PT_ERR_INVALID;
+    uint64_t nr = 0, nt = 0;
+    for (uint32_t li = 0; li < ops->n_logs; li++) {
+        const pt_log_desc& L = ops->logs[li];
+        const pt_insdel_rec* r = ops->insdel + L.insdel_off;
+        run_off[li] = nr; tok_off[li] = nt;
+        uint32_t i = 0;
+        while (i < L.n_insdel) {
+            const uint32_t kind = PT_PAYLOAD_KIND(r[i].payload);
+            uint32_t j = i + 1;
+            if (kind == PT_KIND_INSERT) {
+                while (j < L.n_insdel && PT_PAYLOAD_KIND(r[j].payload) == PT_KIND_INSERT && r[j].actor == r[i].actor && r[j].ctr == r[j - 1].ctr + 1 &&
+                       r[j].ref_ctr == r[j - 1].ctr && r[j].ref_actor == r[j - 1].actor && (j - i) < 0x3FFFFFFFu) j++;
+            } else if (kind == PT_KIND_DELETE) {
+                while (j < L.n_insdel && PT_PAYLOAD_KIND(r[j].payload) == PT_KIND_DELETE && r[j].actor == r[i].actor && r[j].ctr == r[j - 1].ctr + 1 &&
+                       r[j].ref_ctr == r[j - 1].ref_ctr + 1 && r[j].ref_actor == r[i].ref_actor && (j - i) < 0x3FFFFFFFu) j++;
+            }
+            if (runs) { pt_run_rec q; q.ctr0 = r[i].ctr; q.ref_ctr = r[i].ref_ctr; q.actor = r[i].actor; q.ref_actor = r[i].ref_actor; q.kind_count = (kind << 30) | (j - i); runs[nr] = q; }
+            if (kind == PT_KIND_INSERT) { if (tokens) for (uint32_t k = i; k < j; k++) tokens[nt + (k - i)] = PT_PAYLOAD_TOKEN(r[k].payload); nt += j - i; }
+            nr++;
+            i = j;
+        }
+    }
+    run_off[ops->n_logs] = nr; tok_off[ops->n_logs] = nt;
+    if (n_runs_out) *n_runs_out = nr;
+    if (n_tokens_out) *n_tokens_out = nt;
+    return PT_OK;
+}
 int pt_batch_adopt_device(pt_batch* b, const pt_packed_ops* ops) { return upload_common(b, ops, true); }
 
 static int enqueue_merge(pt_batch* b) {
@@ -490,7 +609,8 @@ void pt_batch_destroy(pt_batch* b) {
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
-                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_slab, &b->d_retry, &b->d_seq}) d->release();
+                      &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_slab, &b->d_retry, &b->d_seq,
+                      &b->d_runs, &b->d_tokens, &b->d_run_off, &b->d_tok_off}) d->release();
     for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc, &b->h_seq}) h->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libperitext_b200.so")
 _lib = None
 
-EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_adopt_device", "pt_batch_merge", "pt_batch_sync",
+EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_upload_runs", "pt_compress_runs", "pt_batch_adopt_device", "pt_batch_merge", "pt_batch_sync",
            "pt_batch_download", "pt_batch_download_begin", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count", "pt_batch_stats",
            "pt_batch_last_merge_ms", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
 
@@ -29,6 +29,62 @@ class EngineError(RuntimeError):
 class _PackedOps(ctypes.Structure):
     _fields_ = [("n_logs", ctypes.c_uint32), ("logs", ctypes.c_void_p), ("insdel", ctypes.c_void_p),
                 ("n_insdel_total", ctypes.c_uint64), ("marks", ctypes.c_void_p), ("n_mark_total", ctypes.c_uint64)]
+
+
+class _PackedRuns(ctypes.Structure):
+    _fields_ = [("n_logs", ctypes.c_uint32), ("logs", ctypes.c_void_p), ("run_off", ctypes.c_void_p), ("tok_off", ctypes.c_void_p),
+                ("runs", ctypes.c_void_p), ("tokens", ctypes.c_void_p), ("marks", ctypes.c_void_p),
+                ("n_insdel_total", ctypes.c_uint64), ("n_mark_total", ctypes.c_uint64)]
+
+
+RUN_DT = np.dtype([("ctr0", "<u4"), ("ref_ctr", "<u4"), ("actor", "<u2"), ("ref_actor", "<u2"), ("kind_count", "<u4")])
+
+
+class PackedRuns:
+    """Run-compressed wire form of a PackedBatch (include/peritext_b200.h pt_packed_runs): typing runs and consecutive
+    deletes collapse to one 16-byte run record (+ 4 bytes per inserted value)."""
+
+    def __init__(self, desc, run_off, tok_off, runs, tokens, marks, n_insdel_total):
+        self.desc, self.run_off, self.tok_off, self.runs, self.tokens, self.marks = desc, run_off, tok_off, runs, tokens, marks
+        self.n_insdel_total = int(n_insdel_total)
+
+    @property
+    def n_logs(self) -> int:
+        return int(self.desc.shape[0])
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.desc.nbytes + self.run_off.nbytes + self.tok_off.nbytes + self.runs.nbytes + self.tokens.nbytes + self.marks.nbytes)
+
+    def slice_logs(self, a: int, b: int) -> "PackedRuns":
+        """Logs [a, b) as views (pinned memory stays pinned); offsets re-based (small copies of the offset arrays)."""
+        d = self.desc[a:b].copy()
+        ro = self.run_off[a:b + 1].copy(); to = self.tok_off[a:b + 1].copy()
+        r0, r1, t0, t1 = int(ro[0]), int(ro[-1]), int(to[0]), int(to[-1])
+        if len(d):
+            i0, m0 = int(d[0]["insdel_off"]), int(d[0]["mark_off"])
+            m1 = int(d[-1]["mark_off"]) + int(d[-1]["n_mark"]); i1 = int(d[-1]["insdel_off"]) + int(d[-1]["n_insdel"])
+            d["insdel_off"] -= i0; d["mark_off"] -= m0
+        else:
+            i0 = i1 = m0 = m1 = 0
+        return PackedRuns(d, ro - ro[0], to - to[0], self.runs[r0:r1], self.tokens[t0:t1], self.marks[m0:m1], i1 - i0)
+
+
+def compress_runs(batch: PackedBatch, pin=None) -> PackedRuns:
+    """Host-side run compression (pt_compress_runs).  `pin(nbytes_array) -> array` may place the big arrays in pinned memory."""
+    L = load_library()
+    desc = np.ascontiguousarray(batch.desc)
+    insdel = np.ascontiguousarray(batch.insdel)
+    marks = np.ascontiguousarray(batch.marks)
+    ops = _PackedOps(len(desc), desc.ctypes.data, insdel.ctypes.data, len(insdel), marks.ctypes.data, len(marks))
+    n = len(desc)
+    run_off = np.zeros(n + 1, np.uint64); tok_off = np.zeros(n + 1, np.uint64)
+    nr, nt = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _check(L.pt_compress_runs(ctypes.byref(ops), run_off.ctypes.data, tok_off.ctypes.data, None, None, ctypes.byref(nr), ctypes.byref(nt)), "pt_compress_runs")
+    alloc = pin or (lambda a: a)
+    runs = alloc(np.zeros(max(1, nr.value), RUN_DT)); tokens = alloc(np.zeros(max(1, nt.value), np.uint32))
+    _check(L.pt_compress_runs(ctypes.byref(ops), run_off.ctypes.data, tok_off.ctypes.data, runs.ctypes.data, tokens.ctypes.data, ctypes.byref(nr), ctypes.byref(nt)), "pt_compress_runs")
+    return PackedRuns(desc, alloc(run_off), alloc(tok_off), runs[: nr.value], tokens[: nt.value], alloc(marks) if pin else marks, len(insdel))
 
 
 class _SpansView(ctypes.Structure):
@@ -56,6 +112,8 @@ def load_library() -> ctypes.CDLL:
     L.pt_batch_create.argtypes = [ctypes.c_int, vp, vp, ctypes.POINTER(vp)]
     L.pt_batch_upload.argtypes = [vp, vp]
     L.pt_batch_adopt_device.argtypes = [vp, vp]
+    L.pt_batch_upload_runs.argtypes = [vp, vp]
+    L.pt_compress_runs.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.pt_batch_merge.argtypes = [vp]
     L.pt_batch_sync.argtypes = [vp]
     L.pt_batch_download.argtypes = [vp, vp]
@@ -100,6 +158,14 @@ class BatchEngine:
         marks = np.ascontiguousarray(batch.marks)
         ops = self._ops_struct(desc, insdel.ctypes.data, len(insdel), marks.ctypes.data, len(marks))
         _check(self._L.pt_batch_upload(self._h, ctypes.byref(ops)), "pt_batch_upload")
+        self.n_logs = len(desc)
+
+    def upload_runs(self, r: PackedRuns):
+        desc = np.ascontiguousarray(r.desc)
+        st = _PackedRuns(len(desc), desc.ctypes.data, r.run_off.ctypes.data, r.tok_off.ctypes.data, r.runs.ctypes.data if len(r.runs) else 0,
+                         r.tokens.ctypes.data if len(r.tokens) else 0, r.marks.ctypes.data if len(r.marks) else 0, r.n_insdel_total, len(r.marks))
+        self._keep = (desc, r)
+        _check(self._L.pt_batch_upload_runs(self._h, ctypes.byref(st)), "pt_batch_upload_runs")
         self.n_logs = len(desc)
 
     def adopt_device(self, desc: np.ndarray, insdel_dev_ptr: int, n_insdel: int, marks_dev_ptr: int, n_mark: int):
@@ -196,7 +262,8 @@ class PipelinedEngine:
             self._streams = [torch.cuda.Stream(device=device) for _ in range(chunks)]
         self.engines = [BatchEngine(device, stream=s.cuda_stream) for s in self._streams]
 
-    def run(self, batch: PackedBatch, copy: bool = False) -> list[MergedBatch]:
+    def run(self, batch, copy: bool = False) -> list[MergedBatch]:
+        """`batch`: a PackedBatch, or a PackedRuns (run-compressed upload)."""
         n = batch.n_logs
         # cut by records, not by log count, so the chunks carry similar work
         w = np.cumsum(batch.desc["n_insdel"].astype(np.int64) + 2 * batch.desc["n_mark"].astype(np.int64))
@@ -205,7 +272,11 @@ class PipelinedEngine:
         subs = [batch.slice_logs(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
         used = self.engines[: len(subs)]
         for e, sb in zip(used, subs):
-            e.upload(sb); e.merge(); e.download_begin()
+            if isinstance(sb, PackedRuns):
+                e.upload_runs(sb)
+            else:
+                e.upload(sb)
+            e.merge(); e.download_begin()
         return [e.download(copy=copy) for e in used]
 
     def close(self):

@@ -52,3 +52,28 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
                 assert "oracle/" not in txt.replace("tests/", ""), f
+
+
+def test_run_compression_is_lossless():
+    """pt_compress_runs (host code of the C-ABI library): expanding the runs gives back the records bit for bit."""
+    import numpy as np
+    from peritext_b200 import workload
+    from peritext_b200.engine import compress_runs
+    for cfg in ("c2", "c3", "c4"):
+        b = workload.generate(cfg, n_docs=6, ops_per_doc=1500)
+        r = compress_runs(b)
+        out = np.zeros(len(b.insdel), b.insdel.dtype)
+        for li in range(b.n_logs):
+            o, t, k = int(b.desc[li]["insdel_off"]), int(r.tok_off[li]), 0
+            for q in r.runs[int(r.run_off[li]): int(r.run_off[li + 1])]:
+                cnt, kind = int(q["kind_count"]) & 0x3FFFFFFF, int(q["kind_count"]) >> 30
+                for j in range(cnt):
+                    if kind == 0:
+                        out[o + k] = (int(q["ctr0"]) + j, int(q["ref_ctr"]) if j == 0 else int(q["ctr0"]) + j - 1, int(q["actor"]),
+                                      int(q["ref_actor"]) if j == 0 else int(q["actor"]), int(r.tokens[t])); t += 1
+                    else:
+                        out[o + k] = (int(q["ctr0"]) + j, int(q["ref_ctr"]) + j, int(q["actor"]), int(q["ref_actor"]), 1 << 30)
+                    k += 1
+            assert k == int(b.desc[li]["n_insdel"])
+        assert out.tobytes() == b.insdel.tobytes()
+        assert r.nbytes < b.insdel.nbytes + b.marks.nbytes + b.desc.nbytes * 2

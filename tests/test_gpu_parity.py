@@ -163,3 +163,26 @@ def test_pipelined_engine_equals_single_handle():
             assert p.canonical(i) == whole.canonical(k), k
             k += 1
     pipe.close(); eng.close()
+
+
+def test_run_compressed_upload_gives_identical_results():
+    from peritext_b200 import workload
+    from peritext_b200.engine import BatchEngine, PipelinedEngine, compress_runs
+    for cfg in ("c2", "c3", "c4"):
+        batch = workload.generate(cfg, n_docs=12, ops_per_doc=1500)
+        eng = BatchEngine(0)
+        whole = eng.run(batch)
+        runs = compress_runs(batch)
+        eng.upload_runs(runs); eng.merge()
+        viaruns = eng.download()
+        for i in range(batch.n_logs):
+            assert viaruns.canonical(i) == whole.canonical(i), (cfg, i)
+        pipe = PipelinedEngine(0, chunks=3)
+        parts = pipe.run(runs, copy=True)
+        k = 0
+        for p in parts:
+            for i in range(p.results.shape[0]):
+                assert p.canonical(i) == whole.canonical(k), (cfg, k)
+                k += 1
+        assert k == batch.n_logs
+        pipe.close(); eng.close()
