@@ -73,7 +73,7 @@ size_t arena_worst_bytes(uint64_t n, uint64_t m, uint64_t KS) {
     const uint64_t NWr = (n + 31) / 32 + 1;
     A(KS, I); A(NWr, 4); A(NWr, 4); A(NWr, 4); A(NWr, I); A(NWr, I);               // T InsBits HeadBits VisBits HeadPre VisPre
     A(NWr * 32 + 32, 1); A(NWr * 32 + 32, 1);                                      // Other Del
-    A(2 * n + 3, 8); A((2 * n + 9) / 8 + 3, 8);                                    // Node Sub
+    A(2 * n + 3, 8); A((2 * n + 9) / 8 + 3, 8); A((2 * n + 9) / 8 + 3, 8);         // Node Sub Sub2
     A(n + 1, I); A(n + 2, 4); A(n + 2, 4); A(n + 1, I); A(n + 1, 4); A(n + 2, I);  // RunHead PosBase VisBase Prun Key GrpOff
     A(n + 1, I); A(n + 1, I); A(n + 1, I);                                         // Unsorted Sorted SPos
     A(n / 33 + 2, I); A(KS / 32 + 2, 4); A(KS / 32 + 2, I);                        // BigList GBits GPre

@@ -398,7 +398,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         auto al = [](unsigned long long b) -> unsigned long long { return (b + 15ull) & ~15ull; };
         const unsigned long long I = sizeof(Idx);
         const unsigned long long base = (unsigned long long)A.sm_used + 2 * al((M + 2) * 4ull);
-        unsigned long long peak = base + al((E + 1) * 8ull) + al(((E + 7) / 8 + 3) * 8ull) + 5 * al((M + 1) * I) + al((M + 1) * 4ull) + al((M + 2) * I)
+        unsigned long long peak = base + al((E + 1) * 8ull) + 2 * al(((E + 7) / 8 + 3) * 8ull) + 5 * al((M + 1) * I) + al((M + 1) * 4ull) + al((M + 2) * I)
                                  + al((M / 33 + 2) * I) + al(((KS + 31) / 32 + 1) * 4ull) + al(((KS + 31) / 32 + 1) * I);
         if (m) {
             const unsigned long long NWp_ = (N + 32) / 32 + 1, KW_ = (KS + 31) / 32;
@@ -423,6 +423,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     const uint32_t mark2_sm = A.sm_used; const unsigned long long mark2_gm = A.gm_used;   // run-tree temporaries, released after E
     PT_ALLOC(Node, unsigned long long, E + 1);   // E: Euler-tour nodes
     PT_ALLOC(Sub, unsigned long long, (E + 7) / 8 + 3);   // splitter sublist summaries
+    PT_ALLOC(Sub2, unsigned long long, (E + 7) / 8 + 3);  // second buffer for the jumping rounds
     PT_ALLOC(RunHead, Idx, M + 1);
     PT_ALLOC(Prun, Idx, M + 1);
     PT_ALLOC(Key, uint32_t, M + 1);
@@ -518,8 +519,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
 
     // ---- E: Euler tour (enter r = r, exit r = (M+1)+r, r in 0..M) + weighted pointer-jumping list ranking ------------------
     // One 64-bit word per node: next | element weight | visible weight; invariant: the weights of x cover the nodes from
-    // x up to (excluding) next(x).  A node is read and written as ONE aligned 64-bit word, so jumping in place is safe:
-    // whichever version of the successor a thread reads is self-consistent, and the invariant is preserved.
+    // x up to (excluding) next(x).
     for (uint32_t r = tid; r <= M; r += BLOCK) {
         const uint32_t ent = r, ext = (M + 1) + r;
         const uint32_t cnt = GrpCnt[r];
@@ -561,20 +561,20 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         }
         Sub[k] = valid ? (acc | (nx == END ? SPEND : spOf(nx))) : (unsigned long long)SPEND;
     }
-    if (tid == 0) Sub[SPEND] = SPEND;
+    if (tid == 0) { Sub[SPEND] = SPEND; Sub2[SPEND] = SPEND; }
     __syncthreads();
-    {
-        volatile unsigned long long* vs = Sub;
+    {   // pointer jumping over the splitter summaries only, double buffered (race-free)
+        unsigned long long *cur = Sub, *nxt2 = Sub2;
         for (uint32_t span = 1; span < nSp + 1; span <<= 1) {
             for (uint32_t x = tid; x < nSp; x += BLOCK) {
-                const unsigned long long a = vs[x];
-                const uint32_t nx = (uint32_t)(a & kNodeNxtMask);
-                if (nx == SPEND) continue;
-                const unsigned long long b = vs[nx];
-                vs[x] = ((a & ~kNodeNxtMask) + (b & ~kNodeNxtMask)) | (b & kNodeNxtMask);
+                const unsigned long long a = cur[x];
+                const unsigned long long b = cur[(uint32_t)(a & kNodeNxtMask)];      // cur[SPEND] = {SPEND, 0, 0}
+                nxt2[x] = ((a & ~kNodeNxtMask) + (b & ~kNodeNxtMask)) | (b & kNodeNxtMask);
             }
             __syncthreads();
+            unsigned long long* t = cur; cur = nxt2; nxt2 = t;
         }
+        Sub = cur;
     }
     for (uint32_t r = tid; r < M; r += BLOCK) {
         const unsigned long long loc = Node[r];
