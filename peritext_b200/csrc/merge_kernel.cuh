@@ -439,9 +439,9 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     fill<uint32_t, BLOCK>(GrpCnt, M + 2, 0u);
     fill<uint32_t, BLOCK>(GrpCur, M + 2, 0u);
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += BLOCK) {        // compact the run heads: RunHead[run] = record index
-        const uint32_t hw = HeadBits[i >> 5], b = i & 31;
-        if ((hw >> b) & 1u) RunHead[(uint32_t)HeadPre[i >> 5] + __popc(hw & ((1u << b) - 1u))] = (Idx)i;
+    for (uint32_t w = tid; w < NWr; w += BLOCK) {      // compact the run heads: RunHead[run] = record index (one bit word per thread)
+        uint32_t hb = HeadBits[w], rid = HeadPre[w];
+        while (hb) { const uint32_t b = __ffs(hb) - 1; hb &= hb - 1; RunHead[rid++] = (Idx)(w * 32 + b); }
     }
     __syncthreads();
     for (uint32_t rid = tid; rid < M; rid += BLOCK) {  // one thread per run
