@@ -8,13 +8,17 @@
   applied to the host mirror incrementally (their opIds are larger than everything known, so they land right after their
   reference element); remote changes invalidate the mirror and the next access re-materialises on the GPU.
 
-Not built yet: the Patch stream — `applyChange` and `change` return `patches == []`.
+* The Patch stream (`applyChange` / `change` return values) is derived on the host with the
+  order-independent closed forms of `peritext_b200/patches.py` from the element positions the engine materialised and the
+  arrival times this facade recorded — one GPU materialisation per `applyChange`.  (A batched device version is round-2
+  work; this path serves the interactive single-document use of `bridge.ts`.)
 """
 from __future__ import annotations
 
 import copy
 
 from .packing import RangeError, _root_text_list, decode_spans, js_key, pack_logs, parse_op_id, token_str
+from .patches import ArrivalHistory, derive_patch
 
 _default_engine = None
 INCLUSIVE = {"strong": True, "em": True, "comment": False, "link": False}   # markSpec.inclusive, reference src/schema.ts:45-96
@@ -44,8 +48,11 @@ class JsError(Exception):
 class Micromerge:
     contentKey = "text"  # reference src/micromerge.ts:264
 
-    def __init__(self, actorId: str, engine=None):
+    def __init__(self, actorId: str, engine=None, patches: bool = True):
+        """`patches=False`: `applyChange` / `change` return `[]` and do not materialise (bulk ingest: buffer many changes,
+        read the result once)."""
         self.actorId = actorId
+        self._want_patches = patches
         self.clock: dict[str, int] = {}       # :273
         self._seq = 0                         # :269
         self._maxOp = 0                       # :271
@@ -55,6 +62,9 @@ class Micromerge:
         self._cache = None                    # (batch, merged) of the last GPU materialisation
         self._mirror = None                   # host mirror of the text list: [[elemId, deleted, hasAfter, value], ...]
         self._mirror_list = None
+        self._hist = ArrivalHistory()         # arrival times of the current text list's ops (for the Patch closed forms)
+        self._hist_list = None
+        self._root_keys: dict[str, str] = {}  # ROOT map: key -> opId that last won LWW (src/micromerge.ts:584-586)
 
     # -- reference src/micromerge.ts:499-514 --------------------------------------------------------------------------
     def applyChange(self, change: dict) -> list:
@@ -78,7 +88,53 @@ class Micromerge:
         self._applied.append(copy.deepcopy(change))                  # Change objects passed in are not mutated
         self._cache = None
         self._mirror = None
-        return []   # Patch[]: SURVEY.md §8(f) row 1 — not derived by the batch engine yet
+        return self._patches_for(change["ops"], local=False)
+
+    # -- Patch[] of a list of ops that were just appended to the log (closed forms, peritext_b200/patches.py) ------------
+    def _root_op(self, op) -> list:
+        """ROOT-map LWW bookkeeping in arrival order; returns the makeList patch if the op wins (src/micromerge.ts:584-592)."""
+        key = op.get("key")
+        if key is None or op["action"] in ("addMark", "removeMark"):
+            return []
+        cur = self._root_keys.get(key)
+        if cur is None or compareOpIds(cur, op["opId"]) == -1:
+            self._root_keys[key] = op["opId"]
+            if op["action"] == "makeList":
+                if key == "text":
+                    self._hist, self._hist_list = ArrivalHistory(), op["opId"]
+                return [{**op, "path": ["text"]}]
+        return []
+
+    def _patches_for(self, ops, local: bool) -> list:
+        if not self._want_patches:
+            for op in ops:                      # keep the ROOT / arrival bookkeeping consistent, derive nothing
+                obj = op.get("obj") or "_root"
+                if obj == "_root":
+                    self._root_op(op)
+                elif obj == self._hist_list and (op["action"] in ("addMark", "removeMark") or op.get("key") is None):
+                    self._hist.record(op)
+            return []
+        pending, out = [], []
+        for op in ops:
+            obj = op.get("obj") or "_root"
+            if obj == "_root":
+                out.append(("root", self._root_op(op)))
+            elif obj == self._hist_list and (op["action"] in ("addMark", "removeMark") or op.get("key") is None):
+                t, emits = self._hist.record(op)
+                out.append(("list", (op, t, emits)))
+                pending.append(op)
+        if not pending:
+            return [p for kind, ps in out if kind == "root" for p in ps]
+        pos = {e[0]: k for k, e in enumerate(self._meta())}          # final positions (GPU materialisation or local mirror)
+        patches = []
+        for kind, item in out:
+            if kind == "root":
+                patches += item
+            else:
+                op, t, emits = item
+                if emits:
+                    patches += derive_patch(op, t, pos, self._hist)
+        return patches
 
     # -- GPU materialisation --------------------------------------------------------------------------------------------
     def _text_list_id(self):
@@ -236,7 +292,7 @@ class Micromerge:
                 else:
                     raise JsError(f"Not a list: {path}")
         self._cache = None                 # the GPU materialisation (if any) predates the ops generated above
-        return {"change": copy.deepcopy(change), "patches": []}
+        return {"change": copy.deepcopy(change), "patches": self._patches_for(change["ops"], local=True)}
 
     # -- reference src/micromerge.ts:465-477 ------------------------------------------------------------------------------
     def getCursor(self, path, index: int) -> dict:

@@ -5,7 +5,7 @@ import pytest
 from oracle.oracle import Micromerge as OracleMicromerge
 from peritext_b200 import RangeError
 from peritext_b200.micromerge import Micromerge
-from tests.harness import generateDocs, load_kats, run_concurrent
+from tests.harness import accumulatePatches, generateDocs, load_kats, run_concurrent
 
 
 def test_admission_errors_before_mutation():
@@ -13,7 +13,7 @@ def test_admission_errors_before_mutation():
     docs, _, init = generateDocs(OracleMicromerge, "abc")
     c1 = docs[0].change([{"path": ["text"], "action": "insert", "index": 3, "values": ["d"]}])["change"]
     c2 = docs[0].change([{"path": ["text"], "action": "insert", "index": 4, "values": ["e"]}])["change"]
-    m = Micromerge("replica")
+    m = Micromerge("replica", patches=False)      # no GPU on this box: patches need a materialisation
     with pytest.raises(RangeError, match="Missing dependency: change 1 by actor doc1"):
         m.applyChange(docs[1].change([{"path": ["text"], "action": "insert", "index": 0, "values": ["x"]}])["change"])
     m.applyChange(init)
@@ -34,9 +34,11 @@ def test_kats_through_facade():
         run_concurrent(OracleMicromerge, kat, record=rec)
         for log in rec:
             m = Micromerge("replica")
+            patches = []
             for ch in log:
-                assert m.applyChange(ch) == []
+                patches += m.applyChange(ch)
             assert m.getTextWithFormatting(["text"]) == kat["expectedResult"]
+            assert accumulatePatches(patches) == kat["expectedResult"]      # reference test/micromerge.ts:84-85
             assert "".join(m.root["text"]) == "".join(s["text"] for s in kat["expectedResult"])
 
 
@@ -75,7 +77,7 @@ def test_kats_with_ops_generated_by_the_facade():
 @pytest.mark.gpu
 def test_scripted_kats_through_the_facade():
     """The reference's free-form cases (insert/delete, deps clock, comment/link flatten, cursors) through the facade;
-    the Patch expectations of the four patch cases are skipped (Patch stream: SURVEY.md §8(f) row 1)."""
+    including the four exact Patch expectations (Patch stream derived by the facade's closed forms, peritext_b200/patches.py)."""
     for kat in [k for k in load_kats() if k["kind"] == "script"]:
         docs, _, _ = generateDocs(Micromerge, kat["initialText"])
         saved = {}
@@ -87,7 +89,9 @@ def test_scripted_kats_through_the_facade():
                 if "save" in st:
                     saved[st["save"]] = r["change"]
             elif do == "applyChange":
-                doc.applyChange(saved[st["change"]])
+                patches = doc.applyChange(saved[st["change"]])
+                if "expectPatches" in st:
+                    assert patches == st["expectPatches"], kat["name"]      # the four exact Patch KATs (test/micromerge.ts:915-1029)
             elif do == "expectRootText":
                 assert doc.root["text"] == st["value"]
             elif do == "expectRootTextJoined":
@@ -98,3 +102,25 @@ def test_scripted_kats_through_the_facade():
                 saved[st["save"]] = doc.getCursor(["text"], st["index"])
             elif do == "resolveCursor":
                 assert doc.resolveCursor(saved[st["cursor"]]) == st["expect"], kat["name"]
+
+
+@pytest.mark.gpu
+def test_concurrent_kats_entirely_through_the_facade_with_patches():
+    """testConcurrentWrites (reference test/micromerge.ts:46-86) with the facade as the ONLY Micromerge: spans on both
+    replicas AND `accumulatePatches(all patches of a replica) == expected` (the reference's incremental-path check)."""
+    for kat in [k for k in load_kats() if k["kind"] == "concurrent"]:
+        docs, patch_lists = run_concurrent(Micromerge, kat)
+        for d, patches in zip(docs, patch_lists):
+            assert d.getTextWithFormatting(["text"]) == kat["expectedResult"], kat["line"]
+            assert accumulatePatches(patches) == kat["expectedResult"], kat["line"]
+
+
+@pytest.mark.gpu
+def test_facade_patch_stream_equals_oracle_on_fuzz_logs():
+    from tests.harness import fuzz_session
+    for seed in range(4):
+        _, logs, _ = fuzz_session(OracleMicromerge, 8000 + seed, 60, sync_prob=0.7)
+        for log in logs[:2]:
+            f, o = Micromerge("observer"), OracleMicromerge("observer")
+            for ch in log:
+                assert f.applyChange(ch) == o.applyChange(ch)
