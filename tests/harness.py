@@ -147,7 +147,7 @@ _MARKS = ["strong", "em", "link", "comment"]
 
 
 def fuzz_session(Micromerge, seed, n_steps, replicas=3, initial="ABCDE", sync_prob=1.0, full_sync_at_end=True,
-                 max_chars=2, zero_width_prob=0.0):
+                 max_chars=2, zero_width_prob=0.0, remove_comments=True, on_patches=None):
     """Returns (docs, logs, queues): logs[r] = Changes replica r applied (own + remote) in arrival order."""
     rng = _random.Random(seed)
     docs, _, init = generateDocs(Micromerge, initial, replicas)
@@ -167,7 +167,9 @@ def fuzz_session(Micromerge, seed, n_steps, replicas=3, initial="ABCDE", sync_pr
             while pending:
                 ch = pending.pop(0)
                 try:
-                    docs[dst].applyChange(ch)
+                    ps = docs[dst].applyChange(ch)
+                    if on_patches is not None:
+                        on_patches(dst, ps)
                     logs[dst].append(ch)
                     for op in ch["ops"]:
                         if op["action"] == "addMark" and op.get("markType") == "comment":
@@ -209,10 +211,12 @@ def fuzz_session(Micromerge, seed, n_steps, replicas=3, initial="ABCDE", sync_pr
                     op["attrs"] = {"id": cid}
                     seen_comments[t].append(cid)
                 else:
-                    if not seen_comments[t]:
+                    if not seen_comments[t] or not remove_comments:
                         continue
                     op["attrs"] = {"id": rng.choice(seen_comments[t])}
         r = doc.change([op])
+        if on_patches is not None:
+            on_patches(t, r["patches"])
         queues[ids[t]].append(r["change"])
         logs[t].append(r["change"])
         if rng.random() < sync_prob:

@@ -124,3 +124,28 @@ def test_facade_patch_stream_equals_oracle_on_fuzz_logs():
             f, o = Micromerge("observer"), OracleMicromerge("observer")
             for ch in log:
                 assert f.applyChange(ch) == o.applyChange(ch)
+
+
+@pytest.mark.gpu
+def test_reference_fuzz_loop_against_the_facade():
+    """The reference's fuzz harness (test/fuzz.ts:167-280), seeded: three facade replicas make random edits through
+    `change()`, sync pairwise through `applyChange`, and after every step the harness's three assertions hold:
+    accumulatePatches(all patches) == getTextWithFormatting (fuzz.ts:245-246), clocks equal and spans equal after a
+    full sync (fuzz.ts:277-278).  (removeMark of comments is left out: the reference's accumulatePatches drops ALL comments
+    on a comment removeMark — SURVEY.md §9.3 Q5 — and the reference's own fuzz never emits removeMark, fuzz.ts:80.)"""
+    from tests.harness import fuzz_session
+    for seed in (11, 12):
+        all_patches = [[], [], []]
+
+        def on_patches(r, ps):
+            all_patches[r].extend(ps)
+        docs, logs, _ = fuzz_session(Micromerge, seed, 40, remove_comments=False, on_patches=on_patches)
+        # generateDocs' initial patches are not reported through the hook: replay them from the first change
+        spans = [d.getTextWithFormatting(["text"]) for d in docs]
+        assert spans[0] == spans[1] == spans[2]
+        assert docs[0].clock == docs[1].clock == docs[2].clock
+        init = logs[0][0]
+        init_patches = [{"path": ["text"], "action": "insert", "index": k, "values": [op["value"]], "marks": {}}
+                        for k, op in enumerate(o for o in init["ops"] if o["action"] == "set")]
+        for r in range(3):
+            assert accumulatePatches(init_patches + all_patches[r]) == spans[r], (seed, r)
