@@ -46,3 +46,37 @@ def test_ops_to_marks_matches_reference_rules():
     assert ops_to_marks([c1, c2]) == {"comment": [{"id": "a"}, {"id": "b"}]}
     assert ops_to_marks([c1, c2, rm]) == {"comment": [{"id": "a"}]}
     assert ops_to_marks([rm]) == {"comment": []}                                  # quirk Q3
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_patch_stream_typing_runs_two_replicas(seed):
+    # longer inserts (typing chains) and a longer initial text: more tombstone-boundary and overlap cases per log
+    _, logs, _ = fuzz_session(Micromerge, 7500 + seed, 150, replicas=2, max_chars=6, initial="The Peritext editor", sync_prob=0.5)
+    for r, log in enumerate(logs):
+        fresh = Micromerge(f"observer{r}")
+        got = []
+        for ch in log:
+            got += [p for p in fresh.applyChange(ch) if p["action"] != "makeList"]
+        assert got == closed_form_patches(log, fresh.elements(), "1@doc1"), f"replica {r}"
+
+
+def test_patch_kats_closed_form():
+    """The reference's four exact Patch KATs (test/micromerge.ts:915-1029) through the closed forms."""
+    from tests.harness import generateDocs, load_kats
+    for kat in [k for k in load_kats() if k["kind"] == "script" and any("expectPatches" in st for st in k["steps"])]:
+        docs, _, init = generateDocs(Micromerge, kat["initialText"])
+        logs = [[init], [init]]
+        saved = {}
+        for st in kat["steps"]:
+            d = st["doc"] - 1
+            if st["do"] == "change":
+                ch = docs[d].change(st["ops"])["change"]
+                logs[d].append(ch)
+                if "save" in st:
+                    saved[st["save"]] = ch
+            elif st["do"] == "applyChange":
+                docs[d].applyChange(saved[st["change"]])
+                logs[d].append(saved[st["change"]])
+                allp = closed_form_patches(logs[d], docs[d].elements(), "1@doc1")
+                n = len(st["expectPatches"])
+                assert allp[-n:] == st["expectPatches"], kat["name"]
