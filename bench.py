@@ -1,20 +1,24 @@
 #!/usr/bin/env python3
 """bench.py — ops merged/sec of the Peritext op-log apply + flatten hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--docs D] [--impl engine|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4|c2|c3|c5] [--docs D] [--impl engine|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one pass of the hot path (pt_batch_merge: apply every op of every log + flatten to spans + digest) over one
-batch of synthetic logs.  Default workload = BASELINE.json configs[1] ("c2": 1K docs x 10K ops, insert/delete only,
-2 replicas => 2000 logs, 2x10^7 op records, 320 MB of packed input — larger than the 126 MB L2, so consecutive steps
-re-read their input from HBM).  `value` counts op records applied per second summed over docs AND replicas (each
-replica really applies every op in the reference, src/micromerge.ts:513), inputs resident in HBM; `e2e` is the same
-metric through the public API with pinned-host inputs (H2D) and results read back (D2H) inside the timed region.
-N > 1: documents are sharded by doc id, one process per GPU, same per-GPU work ("weak"); the only collective is one
-all-gather of the 32-byte per-log result headers (digests) per step for the convergence check.
+batch of synthetic logs.  Default workload = BASELINE.json configs[3] ("c4": 100K docs x 1K ops fuzz-generated, 3
+concurrent replicas => 300K logs, 3x10^8 op records, 7.15 GB of packed input — the configuration the north star quotes its
+roofline target on; it fits one GPU).  `value` counts op records applied per second summed over docs AND replicas (each
+replica really applies every op in the reference, src/micromerge.ts:513), inputs resident in HBM; `e2e` is the same metric
+through the public C-ABI path with pinned-host inputs (pt_batch_upload, uncompressed) and packed results read back inside
+the timed region.  `extra_configs` (N = 1 only) carries the device-timed numbers of configs[1] and configs[2] (c2, c3).
+
+N > 1: the SAME 100K documents are sharded by doc id across the ranks (peritext_b200.sharding.shard_range — "strong", what
+configs[3] names: "doc-sharded 8xB200"); the path's only exchange is one all-gather of the 32-byte per-log result headers
+(digests) per step for the convergence check, issued on a side stream so that it overlaps the next step's merge.  `weak`
+carries the same measurement with the per-GPU document count held fixed (every rank merges its own 100K documents).
 
 --impl reference: the reference's sequential algorithm (C++ restatement in oracle/, Node.js is unavailable in this
-image) on all host cores, on a bounded sample of the same workload.
+image) on all host cores, on a bounded sample of the same workload.  It never loads the engine library.
 """
 from __future__ import annotations
 
@@ -88,74 +92,183 @@ def ncu_traffic(config, n_docs):
     return None, None
 
 
-def cpu_baseline(batch, budget_s=20.0):
-    """Times the oracle (sequential reference algorithm) on a bounded sample of the same workload, all host cores."""
+def build_checker_only():
+    """The reference arm and the cpu_baseline leg need the oracle and the workload generator, NOT the engine."""
+    import __graft_entry__ as g
+    g.build(load_engine=False)
+
+
+def cpu_replay_rate(batch, threads, repeats=3):
+    """Median-of-`repeats` ops/s of the oracle replay (sequential reference algorithm, one log per thread)."""
     from oracle.packed import replay_packed
+    rates, secs = [], []
+    for _ in range(repeats):
+        _, dt = replay_packed(batch, threads=threads, flatten=True)
+        rates.append(batch.n_ops / dt); secs.append(dt)
+    k = sorted(range(repeats), key=lambda i: rates[i])[repeats // 2]
+    return rates[k], secs[k], rates
+
+
+def cpu_sample_docs(config, n_docs, cores):
+    # bounded sample: the reference is O(N^2) per document, so a step replays a slice of the workload sized for ~5-10 s
+    if config in ("c2", "c3"):
+        return min(n_docs, max(cores, 16))
+    if config == "c4":
+        return min(n_docs, max(cores * 32, 1024))
+    return 1
+
+
+def cpu_baseline(config, n_docs_total, ops_per_doc):
+    from peritext_b200 import workload
     cores = os.cpu_count() or 1
-    R = batch.meta["replicas"]
-    n_logs = batch.n_logs
-    # grow the sample until the run takes long enough to be meaningful but stays bounded
-    sample = min(n_logs, max(R, cores * R))
-    ops_s, info = 0.0, ""
-    t_spent = 0.0
-    while True:
-        sub = batch.select(range(sample))
-        _, dt = replay_packed(sub, threads=cores, flatten=True)
-        t_spent += dt
-        ops_s = sub.n_ops / dt
-        info = f"first {sample} of {n_logs} logs ({sub.n_ops} op records), {dt:.2f} s, apply+flatten, one log per thread"
-        if dt >= budget_s / 4 or sample >= n_logs or t_spent > budget_s:
-            break
-        grow = max(2.0, min(8.0, (budget_s / 2) / max(dt, 1e-3)))
-        sample = min(n_logs, int(sample * grow) // R * R)
-    return ops_s, cores, info
+    sample_docs = cpu_sample_docs(config, n_docs_total, cores)
+    batch = workload.generate(config, n_docs=sample_docs, ops_per_doc=ops_per_doc)
+    rate, dt, rates = cpu_replay_rate(batch, cores)
+    info = (f"first {sample_docs} of {n_docs_total} docs x {batch.meta['replicas']} replicas ({batch.n_ops} op records), median of 3 replays "
+            f"({dt:.2f} s), apply+flatten, one log per thread; C++ restatement of the reference algorithm (Node.js unavailable in image)")
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": info, "per_thread": rate / cores,
+            "runs": [round(r) for r in rates]}
 
 
 def run_reference(args, rank, world):
-    """--impl reference arm: rank 0 only."""
+    """--impl reference arm: rank 0 only; never loads the engine library."""
     if rank != 0:
         return 0
-    import __graft_entry__ as g
-    g.build()
+    build_checker_only()
     from peritext_b200 import workload
     cfg = workload.CONFIGS[args.config]
     n_docs = args.docs or cfg["n_docs"]
     cores = os.cpu_count() or 1
-    # bounded sample: the reference is O(N^2) per document, so a step replays a slice of the workload
-    sample_docs = min(n_docs, max(cores, 16) if args.config in ("c2", "c3") else max(cores * 64, 1024) if args.config == "c4" else 1)
+    sample_docs = cpu_sample_docs(args.config, n_docs, cores)
     batch = workload.generate(args.config, n_docs=sample_docs, ops_per_doc=args.ops_per_doc)
     from oracle.packed import replay_packed
     for _ in range(max(0, min(args.warmup, 1))):
         replay_packed(batch, threads=cores)
-    t = 0.0
+    per_step = []
     for _ in range(args.steps):
         _, dt = replay_packed(batch, threads=cores)
-        t += dt
-    ms = 1e3 * t / max(1, args.steps)
+        per_step.append(dt)
+    ms = 1e3 * sum(per_step) / max(1, args.steps)
     value = batch.n_ops / (ms / 1e3)
+    med = sorted(per_step)[len(per_step) // 2]
     sample = (f"{sample_docs} of {n_docs} docs x {batch.meta['replicas']} replicas per step ({batch.n_ops} op records); C++ restatement "
               f"of the reference algorithm (Node.js unavailable in image), one log per thread")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {cfg['label']}", "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "per_thread": value / cores,
+                             "median_step_value": batch.n_ops / med},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
+class DeviceRun:
+    """One engine handle with a batch resident in HBM; `timed(steps)` = K merges (+ the digest all-gather on a side stream)."""
+
+    def __init__(self, torch, dist, dev, local_rank, world, batch, counts):
+        from peritext_b200.engine import BatchEngine
+        self.torch, self.dist, self.dev, self.world, self.batch = torch, dist, dev, world, batch
+        self.counts, self.max_logs = counts, max(counts)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev)
+        self.eng = BatchEngine(local_rank, stream=self.stream.cuda_stream)
+        self.eng.upload(batch)
+        self.n_logs = batch.n_logs
+
+        class _DevView:   # zero-copy torch view of the engine-owned per-log result headers
+            def __init__(s, ptr, nbytes):
+                s.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+        n = self.n_logs
+        self.res_dev = torch.as_tensor(_DevView(self.eng.device_results_ptr(), n * 32), device=dev) if n else torch.zeros(0, dtype=torch.uint8, device=dev)
+        if world > 1:
+            self.stage = torch.zeros(self.max_logs * 32, dtype=torch.uint8, device=dev)
+            self.gathered = torch.empty(world * self.max_logs * 32, dtype=torch.uint8, device=dev)
+            self.ev_staged = torch.cuda.Event()
+            self.ev_gathered = torch.cuda.Event()
+            self.ev_gathered.record(self.side)
+
+    def step(self):
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            self.eng.merge()
+            if self.world > 1:
+                # the path's only exchange: result headers (digests) for the convergence check; staged so that the all-gather
+                # of step k runs on the side stream while step k+1 merges
+                self.stream.wait_event(self.ev_gathered)
+                self.stage[: self.n_logs * 32].copy_(self.res_dev, non_blocking=True)
+                self.ev_staged.record(self.stream)
+        if self.world > 1:
+            from peritext_b200 import sharding
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.ev_staged)
+                sharding.all_gather_results(self.stage, self.world, out=self.gathered)
+                self.ev_gathered.record(self.side)
+
+    def timed(self, steps, warmup):
+        torch, dist = self.torch, self.dist
+        for _ in range(warmup):
+            self.step()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = self.eng.launch_count
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record(self.stream)
+        for k in range(steps):
+            self.step()
+            evs[k + 1].record(self.stream)
+        end = torch.cuda.Event(enable_timing=True)
+        if self.world > 1:
+            self.stream.wait_event(self.ev_gathered)      # the last step's exchange is inside the timed region
+        end.record(self.stream)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        total = evs[0].elapsed_time(end)
+        per = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(steps))
+        return total, per, self.eng.launch_count - l0
+
+    def lone_merge_ms(self, reps=5):
+        v = []
+        for _ in range(reps):
+            self.eng.merge(); self.eng.sync(); v.append(self.eng.last_merge_ms)
+        return sorted(v)[len(v) // 2]
+
+    def check(self):
+        """(result headers, all statuses ok, replicas converged) over this rank's logs and — after an exchange — every rank's."""
+        from peritext_b200 import sharding
+        R = self.batch.meta["replicas"]
+        results = self.eng.results()
+        rep = sharding.convergence_report(results, R)
+        ok, conv = rep["all_status_ok"], rep["replicas_converged"]
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            allres = sharding.headers_from_bytes(self.gathered.cpu().numpy()).reshape(self.world, self.max_logs)
+            for r in range(self.world):
+                rr = sharding.convergence_report(allres[r, : self.counts[r]], R)
+                ok = ok and rr["all_status_ok"]; conv = conv and rr["replicas_converged"]
+        return results, ok, conv
+
+    def close(self):
+        self.eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
-    ap.add_argument("--docs", type=int, default=0, help="documents per GPU (default: the config's)")
+    ap.add_argument("--config", default="c4", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--docs", type=int, default=0, help="documents in the whole job (default: the config's; c5: 16 per GPU)")
     ap.add_argument("--ops-per-doc", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra configs (c2, c3) reported beside the headline")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
 
@@ -179,170 +292,168 @@ def main():
 
     import __graft_entry__ as g
     g.build()
-    from peritext_b200 import workload
-    from peritext_b200.engine import BatchEngine
-    from peritext_b200.packing import RESULT_DT
+    from peritext_b200 import sharding, workload
+    from peritext_b200.packing import INSDEL_DT, MARK_DT, PackedBatch
 
     cfg = workload.CONFIGS[args.config]
-    n_docs = args.docs or cfg["n_docs"]
+    n_docs_total = args.docs or (cfg["n_docs"] if args.config != "c5" else 16 * world)
+    gen_threads = max(1, (os.cpu_count() or 8) // world)
+
+    # ---- strong: the job's documents sharded by doc id over the ranks --------------------------------------------------
+    first, count = sharding.shard_range(n_docs_total, rank, world)
+    R = cfg["replicas"]
+    counts = [sharding.shard_range(n_docs_total, r, world)[1] * R for r in range(world)]      # logs per rank
     t0 = time.time()
-    batch = workload.generate(args.config, n_docs=n_docs, ops_per_doc=args.ops_per_doc, doc_first=rank * n_docs)
+    batch = workload.generate(args.config, n_docs=count, ops_per_doc=args.ops_per_doc, doc_first=first, threads=gen_threads)
     gen_s = time.time() - t0
-    R = batch.meta["replicas"]
-    n_logs = batch.n_logs
-    ops_per_step_local = batch.n_ops                      # op records applied (docs x replicas)
     in_bytes = batch.insdel.nbytes + batch.marks.nbytes + batch.desc.nbytes
-
-    # pinned host copies of the inputs (the e2e leg uploads from these every step)
-    def pinned(a):
-        t = torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory() if a.nbytes else torch.zeros(16, dtype=torch.uint8).pin_memory()
-        return t
-    p_ins, p_mk = pinned(batch.insdel), pinned(batch.marks)
-    from peritext_b200.packing import INSDEL_DT, MARK_DT, PackedBatch
-    pbatch = PackedBatch(batch.desc,
-                         p_ins.numpy()[: batch.insdel.nbytes].view(INSDEL_DT), p_mk.numpy()[: batch.marks.nbytes].view(MARK_DT),
-                         batch.values, batch.link_attrs, batch.comment_ids, batch.other_attrs, batch.meta)
-
-    # a non-default stream: the engine captures its launch sequence into a CUDA graph (not possible on the legacy stream)
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    eng = BatchEngine(local_rank, stream=stream.cuda_stream)
-    eng.upload(pbatch)
-
-    class _DevView:   # zero-copy torch view of the engine-owned per-log result headers
-        def __init__(self, ptr, nbytes):
-            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-    res_dev = torch.as_tensor(_DevView(eng.device_results_ptr(), n_logs * 32), device=dev) if n_logs else torch.zeros(0, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(world * n_logs * 32, dtype=torch.uint8, device=dev) if world > 1 else None
-
-    def step():
-        eng.merge()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, res_dev)   # the path's only exchange: digests for the convergence check
 
     stop_evt, samples = threading.Event(), []
     th = threading.Thread(target=sample_clocks, args=(stop_evt, samples, local_rank), daemon=True)
     th.start()
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    launches0 = eng.launch_count
-    # keep the GPU busy for a moment so the clock sampler sees the loaded state as well
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-        kernel_ms.append(None)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count - launches0
 
-    # per-launch duration of the dominant kernel: one merge timed alone with the engine's own events
-    lone = []
-    for _ in range(min(5, args.steps)):
-        eng.merge(); eng.sync(); lone.append(eng.last_merge_ms)
+    run = DeviceRun(torch, dist, dev, local_rank, world, batch, counts)
+    total_ms, per_step, launches = run.timed(args.steps, args.warmup)
+    lone_ms = run.lone_merge_ms(min(5, args.steps))
+    results, ok, converged = run.check()
+    stats = run.eng.stats()
+    ops_local = batch.n_ops
+    alg_bytes = batch.algorithmic_bytes(results)
 
-    results = eng.results()
-    ok = bool((results["status"] == 0).all())
-    dig = results["digest"].reshape(n_logs // R, R, 2) if n_logs else np.zeros((0, R, 2), np.uint64)
-    converged = bool((dig == dig[:, :1, :]).all())
-    if world > 1:
-        allres = gathered.cpu().numpy().view(RESULT_DT).reshape(world, n_logs)
-        ok = ok and bool((allres["status"] == 0).all())
-        d2 = allres["digest"].reshape(world, n_logs // R, R, 2)
-        converged = converged and bool((d2 == d2[:, :, :1, :]).all())
-
-    # ---- e2e through the public API: pinned host -> device, merge, results (headers + text + spans) back to host -------
+    # ---- e2e through the public API: pinned host -> device (pt_batch_upload), merge, packed results back to host ----------
     e2e = None
     if not args.no_e2e:
+        from peritext_b200.engine import PipelinedEngine
+
+        def pinned(a):
+            return torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory() if a.nbytes else torch.zeros(16, dtype=torch.uint8).pin_memory()
+        p_ins, p_mk = pinned(batch.insdel), pinned(batch.marks)
+        pbatch = PackedBatch(batch.desc, p_ins.numpy()[: batch.insdel.nbytes].view(INSDEL_DT), p_mk.numpy()[: batch.marks.nbytes].view(MARK_DT),
+                             batch.values, batch.link_attrs, batch.comment_ids, batch.other_attrs, batch.meta)
         # the public batch API: PipelinedEngine cuts the batch into 4 runs of logs (own handle + stream each) so that the
         # upload of one overlaps the merge and the download of the others
-        from peritext_b200.engine import PipelinedEngine, compress_runs
         pipe = PipelinedEngine(local_rank, chunks=4)
-        # the host -> device leg uses the run-compressed wire form (typing runs / consecutive deletes as one record),
-        # expanded on the device; compressed once here, like the packing itself, outside the timed region
-        keep = []
-
-        def pin(a):
-            t = torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory() if a.nbytes else torch.zeros(16, dtype=torch.uint8).pin_memory()
-            keep.append(t)
-            return t.numpy()[: a.nbytes].view(a.dtype)
-        pruns = compress_runs(pbatch, pin=pin)
-        in_bytes_e2e = pruns.nbytes
-        pbatch_e2e = pruns
         outs = None
         for _ in range(2):
-            outs = pipe.run(pbatch_e2e)
+            outs = pipe.run(pbatch)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e_steps = max(3, min(args.steps, 10))
+        e_steps = max(3, min(args.steps, 8))
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            outs = pipe.run(pbatch_e2e)
+            outs = pipe.run(pbatch)
         torch.cuda.synchronize()
         e_ms = 1e3 * (time.perf_counter() - t0) / e_steps
-        d2h = sum(o.results.nbytes + o.text.nbytes + o.spans.nbytes + o.comment_pool.nbytes for o in outs)
+        d2h = sum(o.results.nbytes + o.text.nbytes + o.spans.nbytes + o.comment_pool.nbytes + o.text_off.nbytes + o.span_off.nbytes for o in outs)
         e_res = np.concatenate([o.results for o in outs])
         e2e_ok = bool((e_res["status"] == 0).all()) and e_res["digest"].tobytes() == results["digest"].tobytes()
         ok = ok and e2e_ok
-        e2e = {"ms": e_ms, "h2d": in_bytes_e2e, "d2h": int(d2h)}
+        e2e = {"ms": e_ms, "h2d": int(in_bytes), "d2h": int(d2h)}
         pipe.close()
+        del pbatch, p_ins, p_mk, outs
+
+    # reduce over ranks: time = max, work = sum
+    def reduce_max(*vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def reduce_sum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    t_ms, e2e_ms = reduce_max(total_ms, e2e["ms"] if e2e else 0.0)
+    total_ops = reduce_sum(ops_local)
+    total_logs = reduce_sum(batch.n_logs)
+    ms_per_step = t_ms / args.steps
+    value = total_ops / (ms_per_step / 1e3)
+    n_logs_local = batch.n_logs
+    unique_local = batch.meta["unique_ops"]
+    run.close()
+    del run, batch
+
+    # ---- weak: every rank merges its own full-size batch (N > 1 only) ----------------------------------------------------
+    weak = None
+    if world > 1 and not args.no_weak:
+        per_gpu = n_docs_total
+        wb = workload.generate(args.config, n_docs=per_gpu, ops_per_doc=args.ops_per_doc, doc_first=sharding.weak_doc_first(per_gpu, rank), threads=gen_threads)
+        wrun = DeviceRun(torch, dist, dev, local_rank, world, wb, [wb.n_logs] * world)
+        w_total, w_per, _ = wrun.timed(args.steps, args.warmup)
+        _, w_ok, w_conv = wrun.check()
+        (w_ms,) = reduce_max(w_total)
+        w_ops = reduce_sum(wb.n_ops)
+        weak = {"value": w_ops / (w_ms / args.steps / 1e3), "unit": UNIT, "ms_per_step": w_ms / args.steps, "docs_per_gpu": per_gpu,
+                "all_status_ok": w_ok, "replicas_converged": w_conv}
+        ok = ok and w_ok; converged = converged and w_conv
+        wrun.close()
+        del wrun, wb
+
+    # ---- the other single-GPU configs, device-timed (N = 1 only) ------------------------------------------------------------
+    extras = None
+    if world == 1 and not args.no_extras and args.config == "c4":
+        extras = {}
+        peak, _ = hbm_peak()
+        for name in ("c3", "c2"):
+            xb = workload.generate(name, threads=gen_threads)
+            xr = DeviceRun(torch, dist, dev, local_rank, 1, xb, [xb.n_logs])
+            x_total, x_per, _ = xr.timed(args.steps, args.warmup)
+            x_res, x_ok, x_conv = xr.check()
+            x_ms = x_total / args.steps
+            x_alg = xb.algorithmic_bytes(x_res)
+            extras[name] = {"workload": workload.CONFIGS[name]["label"], "value": xb.n_ops / (x_ms / 1e3), "unit": UNIT, "ms_per_step": x_ms,
+                            "ms_per_step_min": x_per[0], "roofline_frac": x_alg / (x_ms / 1e3) / 1e9 / peak,
+                            "algorithmic_bytes_per_launch": int(x_alg), "all_status_ok": x_ok, "replicas_converged": x_conv,
+                            "kernel_paths": xr.eng.stats()}
+            ok = ok and x_ok; converged = converged and x_conv
+            xr.close()
+            del xr, xb
 
     stop_evt.set(); th.join(timeout=2)
 
-    # reduce over ranks: time = max, work = sum
-    t_ms = elapsed_ms
-    if world > 1:
-        t = torch.tensor([elapsed_ms, e2e["ms"] if e2e else 0.0], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_ms = float(t[0]); e2e_ms = float(t[1])
-    else:
-        e2e_ms = e2e["ms"] if e2e else None
-    total_ops_per_step = ops_per_step_local * world
-    ms_per_step = t_ms / args.steps
-    value = total_ops_per_step / (ms_per_step / 1e3)
-
     if rank == 0:
-        alg_bytes = batch.algorithmic_bytes(results)
-        lone_ms = sorted(lone)[len(lone) // 2]
         peak, peak_src = hbm_peak()
         achieved = alg_bytes / (lone_ms / 1e3) / 1e9
-        traffic, traffic_src = ncu_traffic(args.config, n_docs)
+        traffic, traffic_src = ncu_traffic(args.config, count)
+        warp_share = stats.get("logs_deferred_to_big_bin", 0) == 0 and args.config == "c4"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
-            "config": {"workload": f"{args.config}: {cfg['label']}", "docs_per_gpu": n_docs, "replicas": R,
-                       "logs_per_gpu": n_logs, "op_records_per_step_per_gpu": ops_per_step_local,
-                       "unique_ops_per_gpu": batch.meta["unique_ops"], "input_bytes_per_gpu": in_bytes,
-                       "parallelism": f"doc-sharded x{world}", "l2": "input (%.0f MB) larger than the 126 MB L2; no flush needed" % (in_bytes / 1e6)
+            "config": {"workload": f"{args.config}: {cfg['label']}", "docs_total": n_docs_total, "docs_per_gpu": count, "replicas": R,
+                       "logs_per_gpu": n_logs_local, "op_records_per_step": int(total_ops), "op_records_per_step_per_gpu": ops_local,
+                       "unique_ops_per_gpu": unique_local, "input_bytes_per_gpu": in_bytes,
+                       "parallelism": f"doc-sharded x{world} (strong: shard_range over {n_docs_total} docs)",
+                       "l2": "input (%.0f MB per GPU) larger than the 126 MB L2; no flush needed" % (in_bytes / 1e6)
                        if in_bytes > 130e6 else "input smaller than L2 (steps may hit L2)",
                        "generator_s": round(gen_s, 2), "all_status_ok": ok, "replicas_converged": converged,
-                       "docs_per_sec": (n_logs * world) / (ms_per_step / 1e3), "kernel_paths": eng.stats()},
+                       "docs_per_sec": total_logs / (ms_per_step / 1e3), "kernel_paths": stats,
+                       "ms_per_step_min": per_step[0], "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_max": per_step[-1],
+                       "exchange": "none (1 rank)" if world == 1 else "all-gather of 32-byte result headers per step, side stream, inside the timed region"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "ptk::merge_logs_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "ptk::merge_logs_warp_kernel" if warp_share else "ptk::merge_logs_kernel",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": lone_ms},
             "clocks": clocks_summary(samples),
         }
         if e2e:
-            line["e2e"] = {"value": total_ops_per_step / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
+            line["e2e"] = {"value": total_ops / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]), "ms_per_step": e2e_ms,
-                           "api": "peritext_b200.engine.PipelinedEngine.run on the run-compressed wire form (4 chunks: pt_batch_upload_runs / merge / download_begin / download per chunk)",
-                           "uncompressed_input_bytes": int(in_bytes)}
+                           "api": "peritext_b200.engine.PipelinedEngine.run over the C-ABI, uncompressed wire form (4 chunks: pt_batch_upload / "
+                                  "pt_batch_merge / pt_batch_download_begin [device-side packing of the outputs] / pt_batch_download per chunk)"}
+        if weak:
+            line["weak"] = weak
+        if extras:
+            line["extra_configs"] = extras
         if not args.no_cpu_baseline and world == 1:
-            v, cores, info = cpu_baseline(batch)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": info}
+            line["cpu_baseline"] = cpu_baseline(args.config, n_docs_total, args.ops_per_doc)
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

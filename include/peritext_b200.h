@@ -11,7 +11,10 @@
  *
  * Conventions: plain C types only, no C++/torch types; every function returns a pt_status code (never
  * throws); device work is enqueued on the CUDA stream handle given at create time; host buffers passed
- * in are owned by the caller and may be freed as soon as the call returns.
+ * in are owned by the caller.  PAGEABLE input buffers may be freed as soon as the call returns (the call
+ * waits for the copy); buffers in PINNED (page-locked) memory are read asynchronously by the copy engine and
+ * must stay valid until the next synchronising call on the handle (pt_batch_sync, pt_batch_download*,
+ * pt_batch_last_merge_ms, the next pt_batch_upload*).
  */
 #ifndef PERITEXT_B200_H
 #define PERITEXT_B200_H
@@ -163,20 +166,24 @@ typedef struct pt_span {
 #define PT_SPAN_NCOMMENTS(f) ((uint32_t)(f) >> 8)
 
 /* Host view of a merged batch; pointers are engine-owned pinned host memory, valid until the next
- * pt_batch_upload/pt_batch_destroy on the handle. Log i's tokens start at text_off[i], spans at span_off[i]. */
+ * pt_batch_upload/pt_batch_destroy on the handle. The outputs are PACKED on the device before the copy: log i's
+ * tokens are text[text_off[i] .. text_off[i+1]), its spans spans[span_off[i] .. span_off[i+1]). */
 typedef struct pt_spans_view {
     uint32_t n_logs;
     const pt_log_result* results; /* [n_logs]                                                      */
-    const uint64_t* text_off;     /* [n_logs]                                                      */
-    const uint64_t* span_off;     /* [n_logs]                                                      */
+    const uint64_t* text_off;     /* [n_logs + 1] packed offsets (exclusive scan of n_visible)      */
+    const uint64_t* span_off;     /* [n_logs + 1] packed offsets (exclusive scan of n_spans)        */
     const uint32_t* text;         /* visible element value tokens (PT_PAYLOAD_TOKEN)               */
     const pt_span* spans;
     const uint32_t* comment_pool;
     uint64_t comment_pool_used;
-    const uint32_t* seq;          /* NULL unless PT_FLAG_EMIT_SEQUENCE: per log (offset text_off[i], n_elems entries) the element
+    const uint32_t* seq;          /* NULL unless PT_FLAG_EMIT_SEQUENCE: per log (offset seq_off[i], n_elems entries) the element
                                      sequence incl. tombstones (the reference's `metadata` array, src/micromerge.ts:255):
                                      bits30:0 = index of the element's insert record in the log's ins/del records,
                                      bit31 = deleted                                                                  */
+    const uint64_t* seq_off;      /* [n_logs] offsets into seq (capacity layout: running sum of n_insdel); NULL without seq */
+    uint64_t comment_pool_needed; /* comment-pool entries the whole batch needs; > the pool's capacity iff some logs
+                                     reported PT_LOG_OVERFLOW: call pt_batch_set_comment_pool(needed) and merge again  */
 } pt_spans_view;
 
 /* Engine limits / tuning. Zero-initialise for defaults. */
@@ -202,8 +209,9 @@ typedef struct pt_batch pt_batch; /* opaque; one per (GPU, batch); not thread-sa
  * (a cudaStream_t / CUstream passed as void*, NULL = legacy default stream). */
 int pt_batch_create(int device, const pt_limits* limits, void* cuda_stream, pt_batch** out);
 
-/* Copy a packed batch host -> device (asynchronous on the handle's stream; the host arrays are staged
- * through engine-owned pinned memory, so the caller may free them on return). Replaces any previous batch.
+/* Copy a packed batch host -> device (asynchronous on the handle's stream for pinned inputs, see the buffer
+ * rule above; the descriptors are staged through engine-owned pinned memory). Waits for the handle's previous
+ * work first. Replaces any previous batch.
  * This is the H2D leg of Micromerge.applyChange's input (src/micromerge.ts:499). */
 int pt_batch_upload(pt_batch*, const pt_packed_ops* host_ops);
 
@@ -245,8 +253,15 @@ int pt_batch_device_results(pt_batch*, void** dev_ptr, uint32_t* n_logs);
 uint64_t pt_batch_launch_count(const pt_batch*);
 
 /* Diagnostics of the last merge: out[0] = logs materialised entirely in shared memory, out[1] = logs that were
- * restarted on the spill-capable path (working set larger than the bin's shared-memory budget). Synchronises. */
+ * restarted on the spill-capable path (working set larger than the bin's shared-memory budget), out[2] = logs deferred on
+ * the device to a kernel variant with a larger budget, out[3] = comment-pool entries the batch needs. Synchronises. */
 int pt_batch_stats(pt_batch*, uint64_t out[4]);
+
+/* Resize the comment pool (entries of 4 bytes) of the current batch and of later uploads.  Logs that find the pool full
+ * report PT_LOG_OVERFLOW (which ones depends on scheduling); pt_spans_view.comment_pool_needed / pt_batch_stats out[3]
+ * give the batch's exact demand, so ONE re-merge after pt_batch_set_comment_pool(needed) always succeeds and is
+ * deterministic.  Synchronises. */
+int pt_batch_set_comment_pool(pt_batch*, uint64_t entries);
 
 /* Time of the last pt_batch_merge on the device, in milliseconds (CUDA events recorded on the
  * handle's stream around the launches); <0 if not available. Synchronises. */

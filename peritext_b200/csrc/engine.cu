@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "merge_kernel.cuh"
+#include "warp_kernel.cuh"
 
 namespace {
 
@@ -52,15 +53,19 @@ struct HostBuf {   // pinned
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-constexpr int kNumBins = 4;
+constexpr int kNumBins = 5;
 struct BinCfg { uint32_t max_recs; int block; uint32_t smem; int ctas_per_sm; };
-// shared memory per SM: 228 KB, 1 KB reserved per resident CTA, 227 KB max per CTA
+// shared memory per SM: 228 KB, 1 KB reserved per resident CTA, 227 KB max per CTA.
+// Bin 0 is the WARP-PER-LOG kernel (warp_kernel.cuh): block = warps per CTA * 32, smem = bytes PER WARP; a log it cannot
+// finish is deferred on the device to bin 1.  Bins 1..4 are the CTA-per-log kernel (merge_kernel.cuh).
 BinCfg kBins[kNumBins] = {
+    {2048u, 8 * 32, 6656u, 4},
     {1536u, 128, 31u * 1024u, 7},
     {4096u, 256, 74u * 1024u, 3},
     {12288u, 512, 112u * 1024u, 2},
     {0xFFFFFFFFu, 1024, 226u * 1024u, 1},
 };
+bool g_warp_bin = true, g_warp_force = false;   // force: skip the host-side footprint estimate (tests of the device-side deferral)
 
 inline size_t al16(size_t b) { return (b + 15) & ~(size_t)15; }
 
@@ -133,6 +138,101 @@ __global__ void expand_runs_kernel(const pt_log_desc* __restrict__ desc, const u
     }
 }
 
+
+// ---- output compaction (download path) ---------------------------------------------------------------------------------
+// The merge kernels write each log's tokens / spans at offsets derived from the descriptors alone (capacity = n_insdel
+// tokens, min(n_insdel, 2 n_mark + 1) spans), typically a few percent full (c4: 5 visible characters per 500-record log).
+// Before the device -> host copy the used prefixes are packed back to back: exclusive scan of (n_visible, n_spans) over
+// the logs (block sums -> one-block scan -> offsets), then one warp per log copies its tokens and spans.
+constexpr uint32_t kScanBlock = 1024;
+__global__ void out_block_sums_kernel(const pt_log_result* __restrict__ res, uint32_t n, unsigned long long* __restrict__ bsum) {
+    __shared__ unsigned long long sa[32], sb[32];
+    const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long a = 0, c = 0;
+    if (i < n && res[i].status == 0) { a = res[i].n_visible; c = res[i].n_spans; }
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if (lane == 0) { sa[warp] = a; sb[warp] = c; }
+    __syncthreads();
+    if (warp == 0) {
+        a = sa[lane]; c = sb[lane];
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+        if (lane == 0) { bsum[2 * blockIdx.x] = a; bsum[2 * blockIdx.x + 1] = c; }
+    }
+}
+__global__ void out_scan_blocks_kernel(unsigned long long* bsum, uint32_t nb) {   // one block; exclusive scan in place, totals at [2 nb]
+    __shared__ unsigned long long ca, cb;
+    __shared__ unsigned long long wa[32], wb[32];
+    if (threadIdx.x == 0) { ca = 0; cb = 0; }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long va = i < nb ? bsum[2 * i] : 0ull, vb = i < nb ? bsum[2 * i + 1] : 0ull;
+        unsigned long long a = va, c = vb;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long ya = __shfl_up_sync(0xffffffffu, a, o), yb = __shfl_up_sync(0xffffffffu, c, o);
+            if (lane >= (uint32_t)o) { a += ya; c += yb; }
+        }
+        if (lane == 31) { wa[warp] = a; wb[warp] = c; }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long x = wa[lane], y = wb[lane];
+            const unsigned long long x0 = x, y0 = y;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long yx = __shfl_up_sync(0xffffffffu, x, o), yy = __shfl_up_sync(0xffffffffu, y, o);
+                if (lane >= (uint32_t)o) { x += yx; y += yy; }
+            }
+            wa[lane] = x - x0; wb[lane] = y - y0;
+        }
+        __syncthreads();
+        const unsigned long long ea = ca + wa[warp] + a - va, eb = cb + wb[warp] + c - vb;
+        if (i < nb) { bsum[2 * i] = ea; bsum[2 * i + 1] = eb; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { ca = ea + va; cb = eb + vb; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { bsum[2 * nb] = ca; bsum[2 * nb + 1] = cb; }
+}
+__global__ void out_offsets_kernel(const pt_log_result* __restrict__ res, uint32_t n, const unsigned long long* __restrict__ bsum, uint32_t nb,
+                                   unsigned long long* __restrict__ toff, unsigned long long* __restrict__ soff) {
+    __shared__ unsigned long long wa[32], wb[32];
+    const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long va = 0, vb = 0;
+    if (i < n && res[i].status == 0) { va = res[i].n_visible; vb = res[i].n_spans; }
+    unsigned long long a = va, c = vb;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long ya = __shfl_up_sync(0xffffffffu, a, o), yb = __shfl_up_sync(0xffffffffu, c, o);
+        if (lane >= (uint32_t)o) { a += ya; c += yb; }
+    }
+    if (lane == 31) { wa[warp] = a; wb[warp] = c; }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long x = wa[lane], y = wb[lane];
+        const unsigned long long x0 = x, y0 = y;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long yx = __shfl_up_sync(0xffffffffu, x, o), yy = __shfl_up_sync(0xffffffffu, y, o);
+            if (lane >= (uint32_t)o) { x += yx; y += yy; }
+        }
+        wa[lane] = x - x0; wb[lane] = y - y0;
+    }
+    __syncthreads();
+    if (i < n) { toff[i] = bsum[2 * blockIdx.x] + wa[warp] + a - va; soff[i] = bsum[2 * blockIdx.x + 1] + wb[warp] + c - vb; }
+    if (i == 0) { toff[n] = bsum[2 * nb]; soff[n] = bsum[2 * nb + 1]; }
+}
+__global__ void out_gather_kernel(const pt_log_result* __restrict__ res, uint32_t n, const uint64_t* __restrict__ cap_toff, const uint64_t* __restrict__ cap_soff,
+                                  const unsigned long long* __restrict__ toff, const unsigned long long* __restrict__ soff,
+                                  const uint32_t* __restrict__ text, const pt_span* __restrict__ spans, uint32_t* __restrict__ ctext, pt_span* __restrict__ cspans) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t li = warp; li < n; li += nwarps) {
+        if (res[li].status != 0) continue;
+        const uint32_t nv = res[li].n_visible, ns = res[li].n_spans;
+        const uint32_t* ts = text + cap_toff[li]; uint32_t* td = ctext + toff[li];
+        for (uint32_t k = lane; k < nv; k += 32) td[k] = ts[k];
+        const uint4* ss = reinterpret_cast<const uint4*>(spans + cap_soff[li]); uint4* sd = reinterpret_cast<uint4*>(cspans + soff[li]);
+        for (uint32_t k = lane; k < ns; k += 32) sd[k] = ss[k];
+    }
+}
+
 }  // namespace
 
 struct pt_batch {
@@ -153,10 +253,11 @@ struct pt_batch {
     // device
     DevBuf d_runs, d_tokens, d_run_off, d_tok_off;
     DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_slab, d_retry, d_seq;
+    DevBuf d_bsum, d_ctoff, d_csoff, d_ctext, d_cspans;   // download path: packed outputs + their offsets ([n_logs + 1])
     const pt_insdel_rec* dp_insdel = nullptr;
     const pt_mark_rec* dp_marks = nullptr;
     // pinned host
-    HostBuf h_stage, h_results, h_text, h_spans, h_pool, h_misc, h_seq;
+    HostBuf h_stage, h_results, h_text, h_spans, h_pool, h_misc, h_seq, h_ctoff, h_csoff;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     cudaGraphExec_t graph_exec = nullptr;   // the merge sequence of the current batch, captured once
@@ -169,15 +270,31 @@ struct pt_batch {
 
 namespace {
 
-// PT_BINS="max_recs:block:smem_kb:ctas_per_sm,..." (4 entries, ascending; last max_recs ignored) overrides the bins (tuning)
+// PT_BINS="max_recs:block:smem_kb:ctas_per_sm,..." (4 entries, ascending; last max_recs ignored) overrides the CTA-per-log bins;
+// PT_WARP="max_recs:warps_per_cta:slice_kb:ctas_per_sm" overrides the warp-per-log bin, PT_WARP=0 disables it (tuning)
+const BinCfg kDefaultBins[kNumBins] = {kBins[0], kBins[1], kBins[2], kBins[3], kBins[4]};
 void load_bins_from_env() {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    // re-read whenever the variables change (tests flip PT_WARP between uploads to cross-check the two kernels)
+    static std::string last = "\x01";
+    const char* we = getenv("PT_WARP"); const char* be = getenv("PT_BINS"); const char* fe = getenv("PT_WARP_FORCE");
+    const std::string cur = std::string(we ? we : "") + "|" + (be ? be : "") + "|" + (fe ? fe : "");
+    if (cur == last) return;
+    last = cur;
+    for (int i = 0; i < kNumBins; i++) kBins[i] = kDefaultBins[i];
+    g_warp_bin = true; g_warp_force = fe && atoi(fe) != 0;
+    if (const char* w = getenv("PT_WARP")) {
+        unsigned long a, wp, sl, ct;
+        if (sscanf(w, "%lu:%lu:%lu:%lu", &a, &wp, &sl, &ct) == 4 && (wp == 2 || wp == 4 || wp == 6 || wp == 8 || wp == 12 || wp == 16)) {
+            if (sl < 256) sl *= 1024;                    // slice: KB, or bytes when >= 256
+            sl &= ~(unsigned long)15;
+            if (sl * wp <= 227 * 1024) kBins[0] = BinCfg{(uint32_t)a, (int)wp * 32, (uint32_t)sl, (int)ct};
+        }
+        else if (atoi(w) == 0) g_warp_bin = false;
+    }
     const char* e = getenv("PT_BINS");
     if (!e) return;
     BinCfg tmp[kNumBins];
-    int k = 0;
+    int k = 1;
     const char* p = e;
     while (k < kNumBins && *p) {
         unsigned long a, bl, sm, ct; int used = 0;
@@ -188,7 +305,7 @@ void load_bins_from_env() {
     }
     if (k != kNumBins) return;
     tmp[kNumBins - 1].max_recs = 0xFFFFFFFFu;
-    for (int i = 0; i < kNumBins; i++) kBins[i] = tmp[i];
+    for (int i = 1; i < kNumBins; i++) kBins[i] = tmp[i];
 }
 
 int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
@@ -210,13 +327,21 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
         ncomment_bound += L.n_mark;
         uint64_t recs = (uint64_t)L.n_insdel + L.n_mark;
         uint64_t KS = (uint64_t)L.max_ctr * (L.n_actors ? L.n_actors : 1);
-        int bin = 0; while (recs > kBins[bin].max_recs) bin++;
+        int bin = 1; while (recs > kBins[bin].max_recs) bin++;
         // typical shared-memory need (runs ~ n/6, segments ~ min(2m, n/2)); a wrong guess only costs a device-side deferral
         {
             const uint64_t I = (L.n_insdel < 32000 && L.n_mark < 32000) ? 2 : 4, n_ = L.n_insdel, m_ = L.n_mark;
             const uint64_t seg = std::min<uint64_t>(2 * m_ + 2, n_ / 2 + 2);
             const uint64_t typical = KS * I + 6 * n_ + (m_ ? m_ * (6 * I + 9) + 32 * seg + 4096 : 0);
             while (bin < kNumBins - 1 && typical > kBins[bin].smem) bin++;
+        }
+        // short logs: one warp per log (16-bit keys and indices).  Footprint estimate: id table (compact form with >= 3
+        // actors: one slot per counter + overflow) + bitmaps + run-tree temporaries for ~ n/3 runs; a low guess only costs
+        // a device-side deferral
+        if (g_warp_bin && !(b->limits.flags & PT_FLAG_EMIT_SEQUENCE) && recs <= kBins[0].max_recs && KS < 0xFFFFull) {
+            const uint64_t R_ = L.n_actors ? L.n_actors : 1, n_ = L.n_insdel;
+            const uint64_t idbytes = (R_ >= 3 && R_ <= 30 && n_ <= 2046) ? 2ull * L.max_ctr + 512 : 2 * KS;
+            if (g_warp_force || idbytes + n_ / 2 + 16 * n_ / 3 + 1024 <= kBins[0].smem) bin = 0;
         }
         bins[bin].push_back(i);
         if (KS > 0x7FFFFFFFull) { g_last_error = "max_ctr * n_actors too large; re-rank counters densely on the host"; return PT_ERR_INVALID; }
@@ -299,8 +424,39 @@ int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P, bool retry) {
     b->launches++;
     return PT_OK;
 }
+template <int WARPS>
+int launch_warp_bin_t(pt_batch* b, ptk::BatchParams P) {
+    const BinCfg& cfg = kBins[0];
+    const uint32_t cnt = b->bin_first[1] - b->bin_first[0];
+    const uint32_t per_cta = WARPS * ptk::kWarpGrab;
+    const uint32_t grid = (uint32_t)std::min<size_t>((cnt + per_cta - 1) / per_cta, (size_t)b->num_sms * cfg.ctas_per_sm);
+    uint32_t* counters = (uint32_t*)((char*)b->d_counters.p + 128);
+    uint32_t* lists = (uint32_t*)b->d_retry.p;
+    P.order = (const uint32_t*)b->d_order.p + b->bin_first[0]; P.n_work = cnt; P.n_work_dev = nullptr;
+    P.work_counter = counters + 0;
+    P.slab_bytes = 0;
+    P.retry_list = lists + (size_t)1 * b->n_logs;
+    P.retry_count = counters + 2 * kNumBins + 1;
+    P.smem_arena_bytes = cfg.smem;                       // per warp
+    const int smem = (int)(cfg.smem * WARPS);
+    PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_warp_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ptk::merge_logs_warp_kernel<WARPS><<<grid, WARPS * 32, smem, b->stream>>>(P);
+    PT_CUDA(cudaGetLastError());
+    b->launches++;
+    return PT_OK;
+}
 int launch_bin(pt_batch* b, int k, const ptk::BatchParams& P, bool retry) {
     if (!retry && b->bin_first[k + 1] == b->bin_first[k]) return PT_OK;
+    if (k == 0) {
+        switch (kBins[0].block / 32) {
+            case 2: return launch_warp_bin_t<2>(b, P);
+            case 4: return launch_warp_bin_t<4>(b, P);
+            case 6: return launch_warp_bin_t<6>(b, P);
+            case 8: return launch_warp_bin_t<8>(b, P);
+            case 12: return launch_warp_bin_t<12>(b, P);
+            default: return launch_warp_bin_t<16>(b, P);
+        }
+    }
     switch (kBins[k].block) {
         case 32: return launch_bin_t<32>(b, k, P, retry);
         case 64: return launch_bin_t<64>(b, k, P, retry);
@@ -339,6 +495,7 @@ int pt_batch_create(int device, const pt_limits* limits, void* cuda_stream, pt_b
 static int upload_common(pt_batch* b, const pt_packed_ops* ops, bool adopt) {
     if (!b || !ops || (ops->n_logs && !ops->logs)) return PT_ERR_INVALID;
     PT_CUDA(cudaSetDevice(b->device));
+    PT_CUDA(cudaStreamSynchronize(b->stream));            // the staging buffer and the device arrays of the previous batch are reused
     b->have_batch = false; b->merged = false;
     if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
     b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0; b->dl_begun = false;
@@ -370,6 +527,7 @@ int pt_batch_upload(pt_batch* b, const pt_packed_ops* ops) { return upload_commo
 int pt_batch_upload_runs(pt_batch* b, const pt_packed_runs* rr) {
     if (!b || !rr || (rr->n_logs && (!rr->logs || !rr->run_off || !rr->tok_off))) return PT_ERR_INVALID;
     PT_CUDA(cudaSetDevice(b->device));
+    PT_CUDA(cudaStreamSynchronize(b->stream));            // the staging buffer and the device arrays of the previous batch are reused
     b->have_batch = false; b->merged = false;
     if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
     b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0; b->dl_begun = false;
@@ -457,7 +615,7 @@ static int enqueue_merge(pt_batch* b) {
     P.slab = (char*)b->d_slab.p;
     P.seq = (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) ? (uint32_t*)b->d_seq.p : nullptr;
     P.stats = (unsigned long long*)b->d_counters.p;
-    { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 0u; }
+    { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 0u; }   // CTA bins: 1 = next log -> L2; warp bin: bit0 marks, bit1 next log
     { const char* e = getenv("PT_TMA"); P.use_tma = e ? (uint32_t)atoi(e) : 1u; }
     int rc;
     // ascending bins; a log whose working set does not fit bin k's shared memory is deferred (on the device) to bin k+1;
@@ -534,21 +692,45 @@ int pt_batch_download_results(pt_batch* b, pt_log_result* out, uint32_t n_logs) 
     return PT_OK;
 }
 
-// Enqueue the device -> host copies of every result array (asynchronous, pinned destinations); pt_batch_download then
-// only waits.  Lets a caller overlap one handle's download with another handle's upload / merge.
+// Pack the outputs on the device (see the compaction kernels above) and enqueue the device -> host copies of the per-log
+// headers, the packed offsets and the comment-pool cursor (asynchronous, pinned destinations); pt_batch_download then
+// waits, learns the packed sizes and copies exactly the used tokens / spans / comment ids.  Lets a caller overlap one
+// handle's download with another handle's upload / merge.
 int pt_batch_download_begin(pt_batch* b) {
     if (!b) return PT_ERR_INVALID;
     if (!b->merged) { g_last_error = "download before merge"; return PT_ERR_STATE; }
     int rc;
     const size_t n = b->n_logs;
+    const uint32_t nb = (uint32_t)((n + kScanBlock - 1) / kScanBlock);
     if ((rc = b->h_results.reserve(std::max<size_t>(1, n) * sizeof(pt_log_result)))) return rc;
-    if ((rc = b->h_text.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
-    if ((rc = b->h_spans.reserve(std::max<uint64_t>(1, b->n_span) * sizeof(pt_span)))) return rc;
+    if ((rc = b->h_ctoff.reserve((n + 1) * 8))) return rc;
+    if ((rc = b->h_csoff.reserve((n + 1) * 8))) return rc;
     if ((rc = b->h_misc.reserve(16))) return rc;
-    PT_CUDA(cudaMemcpyAsync(b->h_misc.p, (char*)b->d_counters.p + 64, 8, cudaMemcpyDeviceToHost, b->stream));
-    if (n) PT_CUDA(cudaMemcpyAsync(b->h_results.p, b->d_results.p, n * sizeof(pt_log_result), cudaMemcpyDeviceToHost, b->stream));
-    if (b->n_text) PT_CUDA(cudaMemcpyAsync(b->h_text.p, b->d_text.p, b->n_text * 4, cudaMemcpyDeviceToHost, b->stream));
-    if (b->n_span) PT_CUDA(cudaMemcpyAsync(b->h_spans.p, b->d_spans.p, b->n_span * sizeof(pt_span), cudaMemcpyDeviceToHost, b->stream));
+    if ((rc = b->d_bsum.reserve((size_t)(2 * nb + 2) * 8))) return rc;
+    if ((rc = b->d_ctoff.reserve((n + 1) * 8))) return rc;
+    if ((rc = b->d_csoff.reserve((n + 1) * 8))) return rc;
+    // packed outputs can never exceed the capacities; sized once per batch
+    if ((rc = b->d_ctext.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
+    if ((rc = b->d_cspans.reserve(std::max<uint64_t>(1, b->n_span) * sizeof(pt_span)))) return rc;
+    PT_CUDA(cudaMemcpyAsync(b->h_misc.p, (char*)b->d_counters.p + 64, 8, cudaMemcpyDeviceToHost, b->stream));   // pool cursor = the batch's demand
+    if (n) {
+        const pt_log_result* res = (const pt_log_result*)b->d_results.p;
+        unsigned long long* bsum = (unsigned long long*)b->d_bsum.p;
+        unsigned long long *toff = (unsigned long long*)b->d_ctoff.p, *soff = (unsigned long long*)b->d_csoff.p;
+        out_block_sums_kernel<<<nb, kScanBlock, 0, b->stream>>>(res, (uint32_t)n, bsum);
+        out_scan_blocks_kernel<<<1, 1024, 0, b->stream>>>(bsum, nb);
+        out_offsets_kernel<<<nb, kScanBlock, 0, b->stream>>>(res, (uint32_t)n, bsum, nb, toff, soff);
+        const uint32_t gthreads = 256, ggrid = (uint32_t)std::min<uint64_t>((n * 32 + gthreads - 1) / gthreads, (uint64_t)b->num_sms * 16);
+        out_gather_kernel<<<ggrid, gthreads, 0, b->stream>>>(res, (uint32_t)n, (const uint64_t*)b->d_text_off.p, (const uint64_t*)b->d_span_off.p, toff, soff,
+                                                           (const uint32_t*)b->d_text.p, (const pt_span*)b->d_spans.p, (uint32_t*)b->d_ctext.p, (pt_span*)b->d_cspans.p);
+        PT_CUDA(cudaGetLastError());
+        b->launches += 4;
+        PT_CUDA(cudaMemcpyAsync(b->h_results.p, b->d_results.p, n * sizeof(pt_log_result), cudaMemcpyDeviceToHost, b->stream));
+        PT_CUDA(cudaMemcpyAsync(b->h_ctoff.p, b->d_ctoff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, b->stream));
+        PT_CUDA(cudaMemcpyAsync(b->h_csoff.p, b->d_csoff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, b->stream));
+    } else {
+        ((uint64_t*)b->h_ctoff.p)[0] = 0; ((uint64_t*)b->h_csoff.p)[0] = 0;
+    }
     if (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) {
         if ((rc = b->h_seq.reserve(std::max<uint64_t>(1, b->n_text) * 4))) return rc;
         if (b->n_text) PT_CUDA(cudaMemcpyAsync(b->h_seq.p, b->d_seq.p, b->n_text * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -564,23 +746,29 @@ int pt_batch_download(pt_batch* b, pt_spans_view* out) {
     if (!b->dl_begun && (rc = pt_batch_download_begin(b))) return rc;
     PT_CUDA(cudaStreamSynchronize(b->stream));
     const bool want_seq = (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) != 0;
-    uint64_t used = *(unsigned long long*)b->h_misc.p;
-    if (used > b->pool_cap) used = b->pool_cap;
+    const size_t n = b->n_logs;
+    const uint64_t demand = *(unsigned long long*)b->h_misc.p;
+    const uint64_t used = std::min<uint64_t>(demand, b->pool_cap);
+    const uint64_t n_ctext = ((const uint64_t*)b->h_ctoff.p)[n], n_cspan = ((const uint64_t*)b->h_csoff.p)[n];
     b->pool_used_host = used;
     if ((rc = b->h_pool.reserve(std::max<uint64_t>(1, used) * 4))) return rc;
-    if (used) {
-        PT_CUDA(cudaMemcpyAsync(b->h_pool.p, b->d_pool.p, used * 4, cudaMemcpyDeviceToHost, b->stream));
-        PT_CUDA(cudaStreamSynchronize(b->stream));
-    }
+    if ((rc = b->h_text.reserve(std::max<uint64_t>(1, n_ctext) * 4))) return rc;
+    if ((rc = b->h_spans.reserve(std::max<uint64_t>(1, n_cspan) * sizeof(pt_span)))) return rc;
+    if (n_ctext) PT_CUDA(cudaMemcpyAsync(b->h_text.p, b->d_ctext.p, n_ctext * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (n_cspan) PT_CUDA(cudaMemcpyAsync(b->h_spans.p, b->d_cspans.p, n_cspan * sizeof(pt_span), cudaMemcpyDeviceToHost, b->stream));
+    if (used) PT_CUDA(cudaMemcpyAsync(b->h_pool.p, b->d_pool.p, used * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (n_ctext || n_cspan || used) PT_CUDA(cudaStreamSynchronize(b->stream));
     out->n_logs = b->n_logs;
     out->results = (const pt_log_result*)b->h_results.p;
-    out->text_off = b->h_text_off.data();
-    out->span_off = b->h_span_off.data();
+    out->text_off = (const uint64_t*)b->h_ctoff.p;
+    out->span_off = (const uint64_t*)b->h_csoff.p;
     out->text = (const uint32_t*)b->h_text.p;
     out->spans = (const pt_span*)b->h_spans.p;
     out->comment_pool = (const uint32_t*)b->h_pool.p;
     out->comment_pool_used = used;
     out->seq = want_seq ? (const uint32_t*)b->h_seq.p : nullptr;
+    out->seq_off = want_seq ? b->h_text_off.data() : nullptr;
+    out->comment_pool_needed = demand;                  // the cursor counts past the capacity
     return PT_OK;
 }
 
@@ -600,7 +788,26 @@ int pt_batch_stats(pt_batch* b, uint64_t out[4]) {
     unsigned long long h[8] = {0};
     PT_CUDA(cudaMemcpyAsync(h, b->d_counters.p, 32, cudaMemcpyDeviceToHost, b->stream));
     PT_CUDA(cudaStreamSynchronize(b->stream));
-    for (int i = 0; i < 4; i++) out[i] = h[i];
+    for (int i = 0; i < 3; i++) out[i] = h[i];
+    out[3] = 0;
+    PT_CUDA(cudaMemcpyAsync(h, (char*)b->d_counters.p + 64, 8, cudaMemcpyDeviceToHost, b->stream));
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    out[3] = h[0];                                       // comment-pool entries the batch needs
+    return PT_OK;
+}
+
+int pt_batch_set_comment_pool(pt_batch* b, uint64_t entries) {
+    if (!b) return PT_ERR_INVALID;
+    PT_CUDA(cudaSetDevice(b->device));
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    b->limits.comment_pool_entries = entries;
+    if (b->have_batch && entries) {
+        b->pool_cap = entries;
+        int rc;
+        if ((rc = b->d_pool.reserve(std::max<uint64_t>(1, b->pool_cap) * 4))) return rc;
+        if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }   // the pool pointer / capacity are baked in
+        b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0;
+    }
     return PT_OK;
 }
 
@@ -610,8 +817,8 @@ void pt_batch_destroy(pt_batch* b) {
     cudaStreamSynchronize(b->stream);
     for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
                       &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_slab, &b->d_retry, &b->d_seq,
-                      &b->d_runs, &b->d_tokens, &b->d_run_off, &b->d_tok_off}) d->release();
-    for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc, &b->h_seq}) h->release();
+                      &b->d_runs, &b->d_tokens, &b->d_run_off, &b->d_tok_off, &b->d_bsum, &b->d_ctoff, &b->d_csoff, &b->d_ctext, &b->d_cspans}) d->release();
+    for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc, &b->h_seq, &b->h_ctoff, &b->h_csoff}) h->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);

@@ -206,6 +206,17 @@ __device__ __forceinline__ void digest_flush(BlockCtx<BLOCK>& c, unsigned long l
     if ((threadIdx.x & 31) == 0 && (d0 | d1)) { atomicAdd(&c.dig0, d0); atomicXor(&c.dig1, d1); }
 }
 
+// Comment-pool reservation: ONE fire-and-forget style atomicAdd on the batch-wide cursor (a CAS loop on a hot global word
+// serialises the whole GPU at one success per round trip — measured: 6x slower c4 merges).  The cursor keeps counting past
+// the capacity, so after the merge it holds the batch's exact DEMAND: logs that found the pool full report PT_LOG_OVERFLOW,
+// the host sees demand > capacity (pt_spans_view.comment_pool_needed), resizes once and re-merges — then every log fits.
+template <class Params>
+__device__ __forceinline__ unsigned long long pool_reserve(const Params& P, uint32_t count, uint32_t& status) {
+    const unsigned long long base = atomicAdd(P.comment_used, (unsigned long long)count);
+    if (base + count > P.comment_cap) { status = PT_LOG_OVERFLOW; return 0; }
+    return base;
+}
+
 // Euler-tour node: next (20 bits) | element weight (22 bits) | visible weight (22 bits)
 constexpr uint32_t kNodeNxtBits = 20;
 constexpr unsigned long long kNodeNxtMask = (1ull << kNodeNxtBits) - 1;
@@ -675,7 +686,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             const uint4 r0 = __ldg(q), r1 = __ldg(q + 1);
             // r0 = {ctr, actor|kind<<16|bounds<<24, start_ctr, end_ctr}; r1 = {start_actor|end_actor<<16, attr, arrival, reserved}
             const uint32_t ctr = r0.x, actor = r0.y & 0xFFFFu, kind = (r0.y >> 16) & 0xFFu, bounds = r0.y >> 24;
-            const uint32_t start_ctr = r0.z, end_ctr = r0.w, start_actor = r1.x & 0xFFFFu, end_actor = r1.x >> 16, attr = r1.y;
+            const uint32_t start_ctr = r0.z, end_ctr = r0.w, start_actor = r1.x & 0xFFFFu, end_actor = r1.x >> 16, attr = r1.y, arrival = r1.z;
             uint32_t key = keyOf(ctr, actor);
             uint32_t rank = (uint32_t)KPre[key >> 5] + __popc(KBits[key >> 5] & ((1u << (key & 31)) - 1u));
             MRank[k] = (Idx)rank; ByRank[rank] = (Idx)k; MKind[k] = (uint8_t)kind; MAttr[k] = attr;
@@ -684,12 +695,14 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             const uint32_t NOSLOT = 0xFFFFFFFFu;
             uint32_t ps = NOSLOT, pe = NOSLOT, vs = 0, ve = nvis;
             if (sb <= PT_BOUND_AFTER && !badId(start_ctr, start_actor)) {
+                // the boundary element must have ARRIVED before the mark op: the reference's walk at apply time never matches
+                // an element that is inserted later (peritext.ts:236-241) — a missing start is a no-op, a missing end never ends
                 Idx j = T[keyOf(start_ctr, start_actor)];
-                if (j != NONE) { ps = 2u * posOf(j) + sb; vs = visOf(j) + ((sb && isVis(j)) ? 1u : 0u); }
+                if (j != NONE && (uint32_t)j < arrival) { ps = 2u * posOf(j) + sb; vs = visOf(j) + ((sb && isVis(j)) ? 1u : 0u); }
             }
             if (eb <= PT_BOUND_AFTER && !badId(end_ctr, end_actor)) {
                 Idx j = T[keyOf(end_ctr, end_actor)];
-                if (j != NONE) { pe = 2u * posOf(j) + eb; ve = visOf(j) + ((eb && isVis(j)) ? 1u : 0u); }
+                if (j != NONE && (uint32_t)j < arrival) { pe = 2u * posOf(j) + eb; ve = visOf(j) + ((eb && isVis(j)) ? 1u : 0u); }
             }
             uint32_t a = 0, b = 0;
             if (ps != NOSLOT) {
@@ -843,7 +856,9 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
                 for (uint32_t cj = g0; cj < g1; cj++) {
                     const uint32_t j = CK[cj];
                     if ((uint32_t)IvA[j] <= x && nextEnd <= (uint32_t)IvB[j]) {
-                        const uint32_t rk = (uint32_t)MRank[j] + 1u;
+                        // comment ops fold in Set order = ARRIVAL order, no opId comparison (peritext.ts:314-322, quirk Q4): the
+                        // last-arrived covering op of this id decides; mark records are stored in arrival order
+                        const uint32_t rk = j + 1u;
                         if (rk > best) { best = rk; bestAdd = (MKind[j] & 1u) == 0; }
                     }
                 }
@@ -939,10 +954,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         }
         if (tid == 0) {
             unsigned long long base = 0;
-            if (totalC) {
-                base = atomicAdd(P.comment_used, (unsigned long long)totalC);
-                if (base + totalC > P.comment_cap) { c.status = PT_LOG_OVERFLOW; base = 0; }
-            }
+            if (totalC) base = pool_reserve(P, totalC, c.status);
             c.pool_base = base;
         }
         __syncthreads();

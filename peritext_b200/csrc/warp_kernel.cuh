@@ -1,0 +1,792 @@
+// warp_kernel.cuh — op-log apply + flatten for SHORT logs: ONE WARP materialises one log (sm_100a).
+//
+// Same closed form as merge_kernel.cuh (reference src/micromerge.ts:534-724, src/peritext.ts:154-455),
+// re-cut for logs of up to a few thousand records (BASELINE.json configs[3]: 100K docs x 1K ops x 3 replicas):
+//   * no block barriers: every scan is a shuffle scan, every reduction a redux.sync, phases are separated by __syncwarp;
+//     several warps of a CTA work on different logs, each in its own slice of dynamic shared memory
+//   * 16-bit everything (record indices, opId keys K = (ctr-1)*R + actor, Euler nodes = next:16 | visible weight:16)
+//   * sibling order without sorting groups: run heads are ranked by K with a key-space bitmap (unique keys: counting sort),
+//     then threaded in ASCENDING K with __match_any_sync — the previously threaded sibling of the same parent is the next
+//     sibling in the reference's descending order (src/micromerge.ts:628-635), the last one threaded is the first child
+//   * marks are resolved in VISIBLE space: a mark op covers visible element v iff vis(start slot) <= v < vis(end slot); ops
+//     that cover no visible element (most of them in fuzz-shaped logs, where nearly everything is a tombstone) are dropped
+//     right after their two boundary lookups; spans come from the few survivors by stabbing the elementary segments
+//   * comment ops fold in ARRIVAL order (src/peritext.ts:314-322 has no opId comparison; quirk Q4)
+// A log that does not fit the warp's slice, or whose surviving mark set is too large for the stabbing loops, is DEFERRED on
+// the device to the block kernel's bins (merge_kernel.cuh) — results are identical either way.
+#pragma once
+#include "merge_kernel.cuh"
+
+namespace ptk {
+
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kNone16 = 0xFFFFu;
+constexpr uint32_t kWarpGrab = 4;            // logs taken from the work queue per atomic
+constexpr uint32_t kMaxSegSurvivorWork = 1536;   // ceil(S/32) * nS above this: defer to the block kernel's segment trees
+constexpr uint32_t kMaxCommentSurvivors = 48;    // the comment loops are quadratic in the surviving comment ops
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(kFull, v, o); if (lane >= (uint32_t)o) v += y; }
+    return v;
+}
+
+// per-warp bump allocator over the warp's slice of dynamic shared memory (offsets from the __shared__ symbol: LDS/STS)
+struct WArena {
+    uint32_t base, used, cap; bool overflow;
+    template <class T> __device__ __forceinline__ T* alloc(uint32_t count) {
+        const uint32_t bytes = (uint32_t)((count * sizeof(T) + 15u) & ~15u);
+        const uint32_t off = used; used += bytes;
+        if (used > cap) { overflow = true; used = off; return reinterpret_cast<T*>(ptk_smem + base); }
+        return reinterpret_cast<T*>(ptk_smem + base + off);
+    }
+};
+
+// Phase alignment of the warps of one CTA (optional).  The kernel's code is far larger than the instruction caches
+// (L0 ~6 KB per scheduler, L1.5 32 KB per SM), and warps that drift apart each stream their own part of it from L2; named
+// barriers at a few phase boundaries keep the warps of a CTA in the same code region.  A warp that leaves a log early
+// (error status, deferral, no work) ARRIVES at the remaining barriers without waiting, so nobody waits for it.
+constexpr uint32_t kFirstPhaseBar = 2, kLastPhaseBar = 5;      // barrier 1 = start of a round (work loop)
+__device__ __noinline__ void phase_arrive_rest(uint32_t next, uint32_t nthreads) {
+    for (; next <= kLastPhaseBar; next++) asm volatile("barrier.arrive %0, %1;" ::"r"(next), "r"(nthreads) : "memory");
+}
+struct PhaseSync {
+    uint32_t on, nthreads, next;
+    __device__ __forceinline__ void pass() {
+        if (on) asm volatile("barrier.sync %0, %1;" ::"r"(next), "r"(nthreads) : "memory");
+        next++;
+    }
+    __device__ __forceinline__ void leave() {
+        if (on && next <= kLastPhaseBar) phase_arrive_rest(next, nthreads);
+        next = kLastPhaseBar + 1;
+    }
+};
+
+template <class T>
+__device__ __forceinline__ void wfill(T* p, uint32_t count, T v, uint32_t lane) {   // allocations are padded to 16 B
+    const uint32_t nvec = (uint32_t)((count * sizeof(T) + 15u) >> 4);
+    uint32_t w;
+    if (sizeof(T) == 1) w = 0x01010101u * (uint32_t)(uint8_t)v;
+    else if (sizeof(T) == 2) w = 0x00010001u * (uint32_t)(uint16_t)v;
+    else w = (uint32_t)v;
+    const uint4 q = make_uint4(w, w, w, w);
+    uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll 1
+    for (uint32_t i = lane; i < nvec; i += 32) d[i] = q;
+}
+
+// returns 0: done (result header written), 1: defer to the block kernel
+__device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const uint32_t slice_base, const uint32_t slice_bytes, const uint32_t li_next, PhaseSync ps) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
+
+    // descriptor: all lanes read the same 32 bytes (one broadcast transaction)
+    const uint4 dsc0 = __ldg(reinterpret_cast<const uint4*>(P.desc + li)), dsc1 = __ldg(reinterpret_cast<const uint4*>(P.desc + li) + 1);
+    const unsigned long long insdel_off = (unsigned long long)dsc0.x | ((unsigned long long)dsc0.y << 32);
+    const unsigned long long mark_off = (unsigned long long)dsc0.z | ((unsigned long long)dsc0.w << 32);
+    const uint32_t n = dsc1.x, m = dsc1.y, R = dsc1.z ? dsc1.z : 1u, C = dsc1.w;
+    const unsigned long long KS64 = (unsigned long long)C * R;
+    if (KS64 >= 0xFFFFull || n >= 0xFFFFu || m >= 0xFFFFu) { ps.leave(); return 1; }     // 16-bit keys / indices only
+    const uint32_t KS = (uint32_t)KS64;
+    const pt_insdel_rec* __restrict__ ins = P.insdel + insdel_off;
+    const pt_mark_rec* __restrict__ mk = P.marks + mark_off;
+    uint32_t* text_out = P.text + P.text_off[li];
+    pt_span* span_out = P.spans + P.span_off[li];
+    pt_log_result* res = P.results + li;
+
+    if ((P.prefetch_next & 1u) && m) {       // this log's mark records are needed late: pull them into L2 now
+        const char* p0 = reinterpret_cast<const char*>(mk);
+        const uint32_t lines = (m * (uint32_t)sizeof(pt_mark_rec) + 127u) >> 7;
+        for (uint32_t l = lane; l < lines; l += 32) prefetch_l2(p0 + ((size_t)l << 7));
+    }
+
+    WArena A; A.base = slice_base; A.used = 0; A.cap = slice_bytes; A.overflow = false;
+    uint32_t st = 0;                                           // lane-local status, max-reduced at the checkpoints
+    auto keyOf = [&](uint32_t ctr, uint32_t actor) -> uint32_t { return (ctr - 1u) * R + actor; };
+    auto badId = [&](uint32_t ctr, uint32_t actor) -> bool { return ctr - 1u >= C || actor >= R; };
+    auto fail = [&](uint32_t code) { st = max(st, code); };
+    auto bail = [&](uint32_t code) { if (lane == 0) { pt_log_result r{}; r.status = code; *res = r; } };
+
+    // ---- id table: opId -> insert record index ------------------------------------------------------------------------------
+    // direct : T[K(ctr, actor)], 2 bytes per key of the key space C*R (what merge_kernel.cuh does).
+    // compact: with >= 3 actors most of that space is empty (c4: 250 inserts in 2200 keys), and shared memory per warp is what
+    //          bounds the number of resident warps.  T[ctr-1] = actor:5 | index:11 of ONE insert with that counter; the few
+    //          inserts that share a counter with an earlier one (concurrent edits) go to a small open-addressing overflow
+    //          table OV (key:16 | index:16, linear probing).  More than kOvMax of those: the log is deferred.
+    const bool compact = R >= 3u && R <= 30u && n <= 2046u;
+    constexpr uint32_t kOvSlots = 128, kOvMax = 96, kOvEmpty = 0xFFFFFFFFu;
+    const uint32_t NWr = (n + 31) / 32 + 1;                    // bit words over record indices (+1 zero pad word)
+    uint16_t* T = A.alloc<uint16_t>(compact ? C : KS);
+    uint32_t* OV = A.alloc<uint32_t>(compact ? kOvSlots : 0u);
+    uint32_t* InsBits = A.alloc<uint32_t>(NWr);
+    uint32_t* HeadBits = A.alloc<uint32_t>(NWr);               // first: chain-link bits; after C: run heads
+    uint32_t* VisBits = A.alloc<uint32_t>(NWr);
+    uint16_t* HeadPre = A.alloc<uint16_t>(NWr);
+    uint16_t* VisPre = A.alloc<uint16_t>(NWr);
+    const uint32_t markC = A.used;
+    uint32_t* OtherBits = A.alloc<uint32_t>(NWr);              // element has a child that is not its log successor (dead after C)
+    uint32_t* DelBits = A.alloc<uint32_t>(NWr);                // tombstones (dead after C)
+    if (A.overflow) { ps.leave(); return 1; }
+    wfill<uint16_t>(T, compact ? C : KS, (uint16_t)kNone16, lane);
+    if (compact) wfill<uint32_t>(OV, kOvSlots, kOvEmpty, lane);
+    wfill<uint32_t>(OtherBits, NWr, 0u, lane);
+    wfill<uint32_t>(DelBits, NWr, 0u, lane);
+    if (lane == 0) { InsBits[NWr - 1] = 0; HeadBits[NWr - 1] = 0; }
+    __syncwarp();
+    auto ovHash = [&](uint32_t key) -> uint32_t { return ((key * 40503u) >> 7) & (kOvSlots - 1u); };
+    // index of the insert record with opId (ctr, actor), kNone16 if there is none; the id must be in range (!badId)
+    auto lookup = [&](uint32_t ctr, uint32_t actor) -> uint32_t {
+        if (!compact) return T[keyOf(ctr, actor)];
+        const uint32_t e = T[ctr - 1u];
+        if (e == kNone16) return kNone16;                      // no insert with this counter at all
+        if ((e >> 11) == actor) return e & 0x7FFu;
+        const uint32_t key = keyOf(ctr, actor);
+        for (uint32_t h = ovHash(key);; h = (h + 1u) & (kOvSlots - 1u)) {
+            const uint32_t v = OV[h];
+            if (v == kOvEmpty) return kNone16;
+            if ((v >> 16) == key) return v & 0xFFFFu;
+        }
+    };
+
+    // ---- A+B: one pass over the ins/del records, 32 per trip, two trips in flight ------------------------------------------
+    // A: id table, insert bits, chain-link bits (reference element == the insert at record i-1: compare with the left
+    //    neighbour's key, no lookup).  B: parents of non-chain inserts ("has another child" bits) and deletes (tombstones, OR).
+    //    A referenced element must have arrived EARLIER in the log (src/micromerge.ts:752 throws otherwise).
+    uint32_t nOv = 0;
+    {
+        const uint4 zero4 = make_uint4(0, 0, 0, 0xC0000000u);
+        uint32_t carryK = 0xFFFFFFFFu;                         // key of the last record of the previous trip if it is an insert
+        uint4 ra = lane < n ? ld_rec(ins + lane) : zero4;
+        uint4 rb = 32 + lane < n ? ld_rec(ins + 32 + lane) : zero4;
+#pragma unroll 1
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            const uint4 rc = base + 64 + lane < n ? ld_rec(ins + base + 64 + lane) : zero4;
+            const uint4 r = ra;
+            const uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16, kind = r.w >> 30;
+            bool isIns = false, valid = false, toOv = false, wrote = false;
+            uint32_t key = 0, mine = 0;
+            if (i < n) {
+                if (kind > 1u) fail(PT_LOG_BAD_KIND);
+                else if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
+                else {
+                    valid = true; key = keyOf(ctr, actor);
+                    if (kind == PT_KIND_INSERT) {
+                        isIns = true;
+                        if (!compact) {
+                            if (T[key] != kNone16) fail(PT_LOG_BAD_OPID);      // two inserts with one opId (earlier trip)
+                            T[key] = (uint16_t)i;
+                        } else {
+                            mine = (actor << 11) | i;
+                            const uint32_t e = T[ctr - 1u];
+                            if (e == kNone16) { T[ctr - 1u] = (uint16_t)mine; wrote = true; }
+                            else if ((e >> 11) == actor) fail(PT_LOG_BAD_OPID);
+                            else toOv = true;
+                        }
+                    }
+                }
+            }
+            const uint32_t myK = isIns ? key : 0xFFFFFFFFu;
+            uint32_t prevK = __shfl_up_sync(kFull, myK, 1);
+            if (lane == 0) prevK = carryK;
+            carryK = __shfl_sync(kFull, myK, 31);
+            const bool refOk = ref_ctr != 0 && !badId(ref_ctr, ref_actor);
+            const uint32_t rkey = keyOf(ref_ctr, ref_actor);
+            bool cand = isIns && refOk && rkey == prevK;           // typing-chain link: the reference element is record i-1
+            if (cand && rkey >= key) { fail(PT_LOG_CYCLE); cand = false; }
+            const uint32_t insW = __ballot_sync(kFull, isIns), candW = __ballot_sync(kFull, cand);
+            if (lane == 0) { InsBits[base >> 5] = insW; HeadBits[base >> 5] = candW; }
+            __syncwarp();                                          // the trip's ids are in T
+            if (!compact) {
+                if (isIns && T[key] != (uint16_t)i) fail(PT_LOG_BAD_OPID);   // two inserts with one opId (same trip)
+            } else {
+                if (wrote) {                                       // same counter twice in one trip: one lane owns the slot
+                    const uint32_t e2 = T[ctr - 1u];
+                    if (e2 != mine) { if ((e2 >> 11) == actor) fail(PT_LOG_BAD_OPID); else toOv = true; }
+                }
+                const uint32_t ovW = __ballot_sync(kFull, toOv);
+                if (ovW) {
+                    nOv += __popc(ovW);
+                    if (toOv && nOv <= kOvMax) {
+                        const uint32_t val = (key << 16) | i;
+                        for (uint32_t h = ovHash(key);; h = (h + 1u) & (kOvSlots - 1u)) {
+                            const uint32_t old = atomicCAS(&OV[h], kOvEmpty, val);
+                            if (old == kOvEmpty) break;
+                            if ((old >> 16) == key) { fail(PT_LOG_BAD_OPID); break; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (valid && !cand) {
+                if (ref_ctr == 0) { if (!isIns) fail(PT_LOG_ELEM_NOT_FOUND); }       // insert: child of HEAD
+                else {
+                    const uint32_t j = refOk ? lookup(ref_ctr, ref_actor) : kNone16;
+                    if (j == kNone16 || j >= i) fail(PT_LOG_ELEM_NOT_FOUND);           // must have arrived earlier
+                    else if (isIns && rkey >= key) fail(PT_LOG_CYCLE);
+                    else atomicOr(&(isIns ? OtherBits : DelBits)[j >> 5], 1u << (j & 31));   // deletes: OR, idempotent (micromerge.ts:689)
+                }
+            }
+            ra = rb; rb = rc;
+        }
+    }
+    __syncwarp();
+    ps.pass();                                                     // (2) end of the record pass
+    if (nOv > kOvMax) { ps.leave(); return 1; }                                    // too many concurrent-counter inserts for the compact table
+    st = __reduce_max_sync(kFull, st);
+    if (st) { bail(st); ps.leave(); return 0; }
+
+    // ---- C: runs, bit-parallel: head = insert & (!chain-link | predecessor has another child); visible = insert & !deleted
+    uint32_t M, nvis, N = 0;
+    {
+        uint32_t carryH = 0, carryV = 0, otherCarry = 0;
+        for (uint32_t wb = 0; wb < NWr; wb += 32) {
+            const uint32_t w = wb + lane;
+            uint32_t insW = 0, candW = 0, otherW = 0, delW = 0;
+            if (w < NWr) { insW = InsBits[w]; candW = HeadBits[w]; otherW = OtherBits[w]; delW = DelBits[w]; }
+            const uint32_t up = __shfl_up_sync(kFull, otherW, 1);
+            const uint32_t prevBit = lane ? (up >> 31) : otherCarry;
+            otherCarry = __shfl_sync(kFull, otherW, 31) >> 31;
+            const uint32_t head = insW & (~candW | ((otherW << 1) | prevBit));
+            const uint32_t vis = insW & ~delW;
+            const uint32_t pc = __popc(head) | (__popc(vis) << 16);
+            const uint32_t inc = warp_incl_scan(pc, lane), ex = inc - pc, tot = __shfl_sync(kFull, inc, 31);
+            if (w < NWr) { HeadBits[w] = head; VisBits[w] = vis; HeadPre[w] = (uint16_t)(carryH + (ex & 0xFFFFu)); VisPre[w] = (uint16_t)(carryV + (ex >> 16)); }
+            carryH += tot & 0xFFFFu; carryV += tot >> 16;
+            N += __reduce_add_sync(kFull, (uint32_t)__popc(insW));
+        }
+        M = carryH; nvis = carryV;
+    }
+    A.used = markC;                                                // release OtherBits / DelBits
+    __syncwarp();
+
+    auto runOf = [&](uint32_t i) -> uint32_t {
+        return (uint32_t)HeadPre[i >> 5] + __popc(HeadBits[i >> 5] & (0xFFFFFFFFu >> (31 - (i & 31)))) - 1u;
+    };
+    auto visBefore = [&](uint32_t i) -> uint32_t {
+        return (uint32_t)VisPre[i >> 5] + __popc(VisBits[i >> 5] & ((1u << (i & 31)) - 1u));
+    };
+
+    // ---- D: run tree; E: Euler tour + splitter list ranking of the VISIBLE weights ------------------------------------------
+    const uint32_t E = 2 * (M + 1), END = E;
+    if (E + 1 >= 0xFFFFu) { ps.leave(); return 1; }
+    uint16_t* VisBase = A.alloc<uint16_t>(M + 1);                  // vis(i) = VisBase[run(i)] + visBefore(i)   (mod 2^16)
+    const uint32_t markD = A.used;
+    {
+        // Euler tour nodes: enter(r) = r, exit(r) = (M+1) + r, r in 0..M (M = HEAD).  Next[x]: successor (later: owner
+        // splitter); Wt[r]: visible weight of enter(r) (later: weight prefix inside the owner's sublist); exits weigh 0.
+        const uint32_t nSp = (E + 7) / 8 + 1, SPEND = nSp, KW = (KS + 31) / 32;
+        uint16_t* Next = A.alloc<uint16_t>(E + 1);
+        uint16_t* Wt = A.alloc<uint16_t>(M + 1);
+        uint16_t* HV = A.alloc<uint16_t>(M + 1);                   // run head record index, then visBefore(head)
+        uint16_t* Prun = A.alloc<uint16_t>(M + 1);
+        uint16_t* RKey = A.alloc<uint16_t>(M + 2);                 // key of the run head; dead after the ranking, then:
+        uint16_t* Last = RKey;                                     // last threaded child of run q (q = M: HEAD)
+        uint16_t* ByG = A.alloc<uint16_t>(M + 1);
+        // key bitmap + prefix (ranking of the head keys); dead after the ranking, then the splitter summaries live there
+        const uint32_t uBytes = max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)(((nSp + 1) * 4 + 15) & ~15u));
+        char* U = A.alloc<char>(uBytes);
+        if (A.overflow) { ps.leave(); return 1; }
+        uint32_t* KBits = reinterpret_cast<uint32_t*>(U);
+        uint16_t* KPre = reinterpret_cast<uint16_t*>(U + (((KW + 1) * 4 + 15) & ~15u));
+        uint32_t* Sub = reinterpret_cast<uint32_t*>(U);
+        uint32_t* Sub2 = reinterpret_cast<uint32_t*>(U + (((nSp + 1) * 4 + 15) & ~15u));
+#pragma unroll 1
+        for (uint32_t wb = 0; wb < NWr; wb += 32) {                // compact the run heads (one bit word per lane)
+            const uint32_t w = wb + lane;
+            if (w < NWr) {
+                uint32_t hb = HeadBits[w], rid = HeadPre[w];
+                while (hb) { const uint32_t b = __ffs(hb) - 1; hb &= hb - 1; HV[rid++] = (uint16_t)(w * 32 + b); }
+            }
+        }
+        wfill<uint32_t>(KBits, KW + 1, 0u, lane);
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t rb = 0; rb < M; rb += 32) {                  // one lane per run: extent, parent run, visible weight, key bit
+            const uint32_t r = rb + lane;
+            if (r < M) {
+                const uint32_t i = HV[r], w = i >> 5, b = i & 31;
+                uint32_t stop = (HeadBits[w] | ~InsBits[w]) & ~(0xFFFFFFFFu >> (31 - b));
+                uint32_t ww = w;
+                while (!stop) { ww++; stop = HeadBits[ww] | ~InsBits[ww]; }      // pad word: InsBits == 0 -> stops
+                const uint32_t end = ww * 32 + (__ffs(stop) - 1);
+                const uint4 rec = ld_rec(ins + i);
+                const uint32_t key = keyOf(rec.x, rec.z & 0xFFFFu);
+                const uint32_t p = rec.y == 0 ? n : lookup(rec.y, rec.z >> 16);
+                const uint32_t q = p == n ? M : runOf(p);
+                const uint32_t hv = visBefore(i);
+                Wt[r] = (uint16_t)(visBefore(end) - hv);
+                HV[r] = (uint16_t)hv;
+                Prun[r] = (uint16_t)q; RKey[r] = (uint16_t)key;
+                atomicOr(&KBits[key >> 5], 1u << (key & 31));
+            }
+        }
+        __syncwarp();
+        {
+            uint32_t carry = 0;
+#pragma unroll 1
+            for (uint32_t wb = 0; wb < KW; wb += 32) {
+                const uint32_t w = wb + lane;
+                const uint32_t cnt = w < KW ? __popc(KBits[w]) : 0u;
+                const uint32_t inc = warp_incl_scan(cnt, lane);
+                if (w < KW) KPre[w] = (uint16_t)(carry + inc - cnt);
+                carry += __shfl_sync(kFull, inc, 31);
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t rb = 0; rb < M; rb += 32) {                  // rank of the run head's key among all run heads (unique keys)
+            const uint32_t r = rb + lane;
+            if (r < M) {
+                const uint32_t key = RKey[r];
+                ByG[(uint32_t)KPre[key >> 5] + __popc(KBits[key >> 5] & ((1u << (key & 31)) - 1u))] = (uint16_t)r;
+            }
+        }
+        __syncwarp();
+        ps.pass();                                                 // (3) run heads ranked
+        wfill<uint16_t>(Last, M + 2, (uint16_t)kNone16, lane);     // RKey, KBits, KPre are dead from here
+        if (lane == 0) { Sub[SPEND] = SPEND; Sub2[SPEND] = SPEND; }
+        __syncwarp();
+        // thread the runs in ASCENDING key order: among the children of one parent, the previously threaded one is the
+        // NEXT sibling in descending-opId order (src/micromerge.ts:628-635), the last one threaded is the FIRST child
+#pragma unroll 1
+        for (uint32_t cb = 0; cb < M; cb += 32) {
+            const uint32_t pos = cb + lane;
+            const bool valid = pos < M;
+            const uint32_t r = valid ? (uint32_t)ByG[pos] : 0u;
+            const uint32_t q = valid ? (uint32_t)Prun[r] : (0x10000u + lane);
+            const uint32_t mask = __match_any_sync(kFull, q);
+            const uint32_t lower = mask & lt;
+            const uint32_t src = lower ? (31u - __clz(lower)) : lane;
+            const uint32_t rs = __shfl_sync(kFull, r, src);
+            uint32_t ns = kNone16;
+            if (valid) ns = lower ? rs : (uint32_t)Last[q];
+            __syncwarp();
+            if (valid) {
+                Next[(M + 1) + r] = (uint16_t)(ns != kNone16 ? ns : (M + 1) + q);   // exit(r): next sibling, else exit(parent)
+                if (((mask >> lane) >> 1) == 0) Last[q] = (uint16_t)r;              // highest lane of its group
+            }
+            __syncwarp();
+        }
+#pragma unroll 1
+        for (uint32_t rb = 0; rb <= M; rb += 32) {                 // enter(r): first child, else exit(r)
+            const uint32_t r = rb + lane;
+            if (r <= M) { const uint32_t f = Last[r]; Next[r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); }
+        }
+        if (lane == 0) { Wt[M] = 0; Next[(M + 1) + M] = (uint16_t)END; Next[END] = (uint16_t)END; }
+        __syncwarp();
+        // splitter list ranking: every 8th node id (and the tour's first node) walks its sublist once; only the splitter
+        // summaries are ranked by pointer jumping; suffix(x) = suffix(owner sublist) - prefix(x)
+        const uint32_t headNode = M;
+        auto spOf = [&](uint32_t x) -> uint32_t { return (x & 7u) == 0 ? (x >> 3) : nSp - 1; };
+        auto isSp = [&](uint32_t x) -> bool { return (x & 7u) == 0 || x == headNode; };
+#pragma unroll 1
+        for (uint32_t kb = 0; kb < nSp; kb += 32) {
+            const uint32_t k = kb + lane;
+            if (k < nSp) {
+                uint32_t cur = k + 1 < nSp ? 8 * k : headNode, acc = 0, nx = END;
+                const bool valid = cur < E && (k + 1 < nSp || (headNode & 7u) != 0);
+                if (valid) {
+                    for (;;) {
+                        nx = Next[cur];
+                        Next[cur] = (uint16_t)k;                   // owner
+                        if (cur <= M) { const uint32_t wv = Wt[cur]; Wt[cur] = (uint16_t)acc; acc += wv; }   // prefix before this node
+                        if (nx == END || isSp(nx)) break;
+                        cur = nx;
+                    }
+                }
+                Sub[k] = valid ? ((acc << 16) | (nx == END ? SPEND : spOf(nx))) : SPEND;
+            }
+        }
+        __syncwarp();
+        {
+            uint32_t *cur = Sub, *nxt2 = Sub2;
+            for (uint32_t span = 1; span < nSp + 1; span <<= 1) {
+#pragma unroll 1
+                for (uint32_t x = lane; x < nSp; x += 32) {
+                    const uint32_t a = cur[x], b = cur[a & 0xFFFFu];
+                    nxt2[x] = ((a & 0xFFFF0000u) + (b & 0xFFFF0000u)) | (b & 0xFFFFu);
+                }
+                __syncwarp();
+                uint32_t* t = cur; cur = nxt2; nxt2 = t;
+            }
+            Sub = cur;
+        }
+#pragma unroll 1
+        for (uint32_t rb = 0; rb < M; rb += 32) {
+            const uint32_t r = rb + lane;
+            if (r < M) {
+                const uint32_t suf = (Sub[Next[r]] >> 16) - (uint32_t)Wt[r];        // visible elements from run r to the end
+                VisBase[r] = (uint16_t)((nvis - suf) - (uint32_t)HV[r]);
+            }
+        }
+        __syncwarp();
+    }
+    A.used = markD;                                                // release the run-tree temporaries
+    ps.pass();                                                     // (4) sequence ranked
+    auto visOf = [&](uint32_t i) -> uint32_t { return ((uint32_t)VisBase[runOf(i)] + visBefore(i)) & 0xFFFFu; };
+    auto isVis = [&](uint32_t i) -> bool { return (VisBits[i >> 5] >> (i & 31)) & 1u; };
+
+    // ---- F: text out (visible index = prefix count of non-deleted elements, micromerge.ts:747-750) -------------------------
+    unsigned long long d0 = 0, d1 = 0;
+#pragma unroll 1
+    for (uint32_t w = 0; w + 1 < NWr; w++) {
+        const uint32_t vb = VisBits[w];                            // uniform
+        if (!vb) continue;
+        if ((vb >> lane) & 1u) {
+            const uint32_t i = w * 32 + lane;
+            const uint32_t tok = PT_PAYLOAD_TOKEN(__ldg(&ins[i].payload));
+            const uint32_t vr = visOf(i);
+            text_out[vr] = tok;
+            digest_add(d0, d1, pt_term_text(vr, tok));
+        }
+    }
+
+    uint32_t nspans = 0;
+    if ((P.prefetch_next & 2u) && li_next != 0xFFFFFFFFu) {        // the next log's ins/del records -> L2 while this one does its marks
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(P.desc + li_next)), q1 = __ldg(reinterpret_cast<const uint4*>(P.desc + li_next) + 1);
+        const char* p0 = reinterpret_cast<const char*>(P.insdel + ((unsigned long long)q0.x | ((unsigned long long)q0.y << 32)));
+        const uint32_t lines = (q1.x * (uint32_t)sizeof(pt_insdel_rec) + 127u) >> 7;
+        for (uint32_t l = lane; l < lines; l += 32) prefetch_l2(p0 + ((size_t)l << 7));
+    }
+
+    uint32_t nS = 0, nC = 0;
+    uint4* Sv = nullptr;                                           // survivors: {va | vb << 16, priority:16 | kind << 16, attr, -}
+    uint16_t* CIdx = nullptr;                                      // surviving comment ops (indices into Sv), arrival order
+    if (m) {
+        // ---- G: mark ops -> visible intervals [va, vb); only ops that cover a visible element survive ---------------------
+        const uint32_t KW = (KS + 31) / 32;
+        uint32_t* KBits = A.alloc<uint32_t>(KW + 1);               // duplicate mark opIds
+        CIdx = A.alloc<uint16_t>(kMaxCommentSurvivors + 32);
+        if (A.overflow) { ps.leave(); return 1; }
+        const uint32_t room = A.cap - A.used, svStart = A.used;
+        uint32_t capS = room > 256u ? (room - 256u) / 16u : 0u;
+        if (capS > m) capS = m;
+        Sv = A.alloc<uint4>(capS + 1);
+        if (A.overflow) { ps.leave(); return 1; }
+        wfill<uint32_t>(KBits, KW + 1, 0u, lane);
+        __syncwarp();
+        const uint4* mq = reinterpret_cast<const uint4*>(mk);
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+        if (lane < m) { a0 = __ldg(mq + 2 * lane); a1 = __ldg(mq + 2 * lane + 1); }
+#pragma unroll 1
+        for (uint32_t kb = 0; kb < m; kb += 32) {
+            const uint32_t k = kb + lane;
+            uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+            if (k + 32 < m) { b0 = __ldg(mq + 2 * (size_t)(k + 32)); b1 = __ldg(mq + 2 * (size_t)(k + 32) + 1); }
+            // a0 = {ctr, actor|kind<<16|bounds<<24, start_ctr, end_ctr}; a1 = {start_actor|end_actor<<16, attr, arrival, reserved}
+            const uint32_t ctr = a0.x, actor = a0.y & 0xFFFFu, kind = (a0.y >> 16) & 0xFFu, bounds = a0.y >> 24;
+            const uint32_t start_ctr = a0.z, end_ctr = a0.w, start_actor = a1.x & 0xFFFFu, end_actor = a1.x >> 16, attr = a1.y, arrival = a1.z;
+            const uint32_t type = (kind >> 1) & 3u;
+            bool surv = false;
+            uint32_t va = 0, vb = 0, key = 0;
+            if (k < m) {
+                if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
+                else {
+                    key = keyOf(ctr, actor);
+                    const uint32_t bit = 1u << (key & 31);
+                    if ((atomicOr(&KBits[key >> 5], bit) & bit) || lookup(ctr, actor) != kNone16) fail(PT_LOG_BAD_OPID);   // duplicate opId
+                    const uint32_t sb = bounds & 3u, eb = (bounds >> 2) & 3u;
+                    // a boundary element must exist AND have arrived before the mark op: the reference's walk never matches
+                    // anything else (peritext.ts:236-241) — a missing start is a no-op, a missing end never ends
+                    if (sb <= PT_BOUND_AFTER && !badId(start_ctr, start_actor)) {
+                        const uint32_t js = lookup(start_ctr, start_actor);
+                        if (js != kNone16 && js < arrival) {
+                            va = visOf(js) + ((sb && isVis(js)) ? 1u : 0u);
+                            vb = nvis;
+                            if (eb <= PT_BOUND_AFTER && !badId(end_ctr, end_actor)) {
+                                const uint32_t je = lookup(end_ctr, end_actor);
+                                // same slot: the start branch wins and the op never ends (quirk Q2)
+                                if (je != kNone16 && je < arrival && !(je == js && eb == sb)) vb = visOf(je) + ((eb && isVis(je)) ? 1u : 0u);
+                            }
+                            surv = va < vb;
+                        }
+                    }
+                }
+            }
+            const bool isC = surv && type == PT_MARK_COMMENT;
+            const uint32_t bal = __ballot_sync(kFull, surv), balC = __ballot_sync(kFull, isC);
+            if (surv) {
+                const uint32_t idx = nS + __popc(bal & lt);
+                if (idx < capS) {
+                    // priority: LWW types compare opIds (peritext.ts:304-313) = keys; comments fold in arrival order (Q4)
+                    Sv[idx] = make_uint4(va | (vb << 16), (type == PT_MARK_COMMENT ? k : key) | (kind << 16), attr, 0u);
+                    if (isC) { const uint32_t ci = nC + __popc(balC & lt); if (ci <= kMaxCommentSurvivors) CIdx[ci] = (uint16_t)idx; }
+                }
+            }
+            nS += __popc(bal); nC += __popc(balC);
+            a0 = b0; a1 = b1;
+        }
+        __syncwarp();
+        st = __reduce_max_sync(kFull, st);
+        if (st) { bail(st); ps.leave(); return 0; }
+        if (nS > capS) { ps.leave(); return 1; }
+        A.used = svStart + ((nS * 16u + 15u) & ~15u);               // keep only the survivors
+    }
+
+    ps.pass();                                                     // (5) marks resolved
+    unsigned long long pool_base = 0;
+    if (nvis == 0) nspans = 0;
+    else if (nS == 0) {
+        // no mark op touches a visible element: one span {} (peritext.ts:392)
+        if (lane == 0) {
+            pt_span s; s.start = 0; s.flags = 0; s.link_attr = PT_ATTR_NONE; s.comment_off = 0;
+            span_out[0] = s;
+            digest_add(d0, d1, pt_term_span(0, 0, 0, PT_ATTR_NONE));
+        }
+        nspans = 1;
+    } else {
+        // ---- I: elementary segments of the visible text -> marks per segment -> spans ---------------------------------------
+        if (nC > kMaxCommentSurvivors) { ps.leave(); return 1; }
+        const uint32_t BW = nvis / 32 + 1;
+        uint32_t* Bnd = A.alloc<uint32_t>(BW + 1);
+        uint16_t* BPre = A.alloc<uint16_t>(BW + 1);
+        if (A.overflow) { ps.leave(); return 1; }
+        wfill<uint32_t>(Bnd, BW + 1, 0u, lane);
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t s = lane; s < nS; s += 32) {
+            const uint32_t ab = Sv[s].x, va = ab & 0xFFFFu, vb = ab >> 16;
+            atomicOr(&Bnd[va >> 5], 1u << (va & 31));
+            if (vb < nvis) atomicOr(&Bnd[vb >> 5], 1u << (vb & 31));
+        }
+        __syncwarp();
+        uint32_t nB = 0;
+#pragma unroll 1
+        for (uint32_t wb = 0; wb < BW; wb += 32) {
+            const uint32_t w = wb + lane;
+            const uint32_t cnt = w < BW ? __popc(Bnd[w]) : 0u;
+            const uint32_t inc = warp_incl_scan(cnt, lane);
+            if (w < BW) BPre[w] = (uint16_t)(nB + inc - cnt);
+            nB += __shfl_sync(kFull, inc, 31);
+        }
+        const uint32_t S = nB + 1;                                   // segment s >= 1 starts at the s-th boundary; segment 0 = [0, first)
+        if (((S + 31) / 32) * nS > kMaxSegSurvivorWork) { ps.leave(); return 1; }
+        uint16_t* SegStart = A.alloc<uint16_t>(S + 1);
+        uint32_t* SegFlags = A.alloc<uint32_t>(S + 1);               // bits3:0 span flags, bit4 comment set differs from x-1, bit5 head
+        uint32_t* SegLink = A.alloc<uint32_t>(S + 1);
+        uint16_t* SegCnt = A.alloc<uint16_t>(S + 1);                 // comment ids of the span starting here
+        uint16_t* SegOut = A.alloc<uint16_t>(S + 1);                 // span index
+        uint32_t* SegCOff = A.alloc<uint32_t>(S + 1);                // offset of its comment list in the log's pool reservation
+        if (A.overflow) { ps.leave(); return 1; }
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t wb = 0; wb < BW; wb += 32) {
+            const uint32_t w = wb + lane;
+            if (w < BW) {
+                uint32_t bb = Bnd[w], id = (uint32_t)BPre[w] + 1u;
+                while (bb) { const uint32_t b = __ffs(bb) - 1; bb &= bb - 1; SegStart[id++] = (uint16_t)(w * 32 + b); }
+            }
+        }
+        if (lane == 0) SegStart[0] = 0;
+        const bool seg0_empty = (Bnd[0] & 1u) != 0;                  // position 0 is itself a boundary
+        __syncwarp();
+        // pass 1: marks of every segment = stabbing query over the survivors (uniform loop, broadcast reads)
+#pragma unroll 1
+        for (uint32_t sb = 0; sb < S; sb += 32) {
+            const uint32_t s = sb + lane;
+            const uint32_t x = s < S ? (uint32_t)SegStart[s] : 0u;
+            uint32_t w0 = 0, w1 = 0, w2 = 0, flags = 0, link = PT_ATTR_NONE;
+#pragma unroll 1
+            for (uint32_t j = 0; j < nS; j++) {
+                const uint4 sv = Sv[j];                              // one broadcast LDS.128
+                const uint32_t ab = sv.x, pk = sv.y;
+                const bool cover = x >= (ab & 0xFFFFu) && x < (ab >> 16);
+                const uint32_t t = (pk >> 17) & 3u, val = (((pk & 0xFFFFu) << 16) | j) + 1u;
+                if (cover) {
+                    if (t == PT_MARK_STRONG) w0 = max(w0, val);
+                    else if (t == PT_MARK_EM) w1 = max(w1, val);
+                    else if (t == PT_MARK_LINK) w2 = max(w2, val);
+                    else flags |= PT_SPAN_COMMENT;                   // `comment` key present iff any comment op covers (quirk Q3)
+                }
+            }
+            // LWW winners (peritext.ts:304-313): the max-opId covering op of the type; present iff it is an addMark
+            if (w0 && !((Sv[(w0 - 1u) & 0xFFFFu].y >> 16) & 1u)) flags |= PT_SPAN_STRONG;
+            if (w1 && !((Sv[(w1 - 1u) & 0xFFFFu].y >> 16) & 1u)) flags |= PT_SPAN_EM;
+            if (w2) { const uint32_t j2 = (w2 - 1u) & 0xFFFFu; if (!((Sv[j2].y >> 16) & 1u)) { flags |= PT_SPAN_LINK; link = Sv[j2].z; } }
+            // comment ids differ between x-1 and x?  only ids with a boundary exactly at x can change; presence of an id =
+            // "its last-arrived covering op is an add" (peritext.ts:314-322)
+            if (nC) {
+                const bool live = s >= 1 && s < S && x > 0;
+                bool cd = false;
+                for (uint32_t cj = 0; cj < nC; cj++) {
+                    const uint32_t j = CIdx[cj], ab = Sv[j].x;
+                    const bool touch = live && ((ab & 0xFFFFu) == x || (ab >> 16) == x);
+                    if (!__any_sync(kFull, touch)) continue;
+                    const uint32_t id = Sv[j].z;
+                    bool pPrev = false, pCur = false;
+                    for (uint32_t c2 = 0; c2 < nC; c2++) {
+                        const uint32_t j2 = CIdx[c2];
+                        const uint4 s2 = Sv[j2];
+                        if (s2.z != id) continue;                    // uniform
+                        const uint32_t a2 = s2.x & 0xFFFFu, b2 = s2.x >> 16;
+                        const bool add2 = !((s2.y >> 16) & 1u);
+                        if (x - 1u >= a2 && x - 1u < b2) pPrev = add2;
+                        if (x >= a2 && x < b2) pCur = add2;
+                    }
+                    if (touch && pPrev != pCur) cd = true;
+                }
+                if (cd) flags |= 16u;
+            }
+            if (s < S) { SegFlags[s] = flags; SegLink[s] = link; }
+        }
+        __syncwarp();
+        // pass 2: span heads, span indices, comment counts
+        uint32_t totalC = 0;
+#pragma unroll 1
+        for (uint32_t sb = 0; sb < S; sb += 32) {
+            const uint32_t s = sb + lane;
+            bool head = false;
+            uint32_t cnt = 0;
+            const uint32_t x = s < S ? (uint32_t)SegStart[s] : 0u;
+            if (s < S) {
+                const uint32_t f = SegFlags[s];
+                if (s == 0) head = !seg0_empty;
+                else if (x == 0) head = true;
+                else head = ((f ^ SegFlags[s - 1]) & 0xFu) != 0 || SegLink[s] != SegLink[s - 1] || (f & 16u);
+            }
+            if (nC) {
+                for (uint32_t cj = 0; cj < nC; cj++) {               // members: ids whose last-arrived covering op is an add
+                    const uint32_t j = CIdx[cj], ab = Sv[j].x, id = Sv[j].z;
+                    const bool cov = head && x >= (ab & 0xFFFFu) && x < (ab >> 16);
+                    if (!__any_sync(kFull, cov)) continue;
+                    bool later = false;
+                    for (uint32_t c2 = cj + 1; c2 < nC; c2++) {
+                        const uint32_t j2 = CIdx[c2];
+                        if (Sv[j2].z != id) continue;
+                        const uint32_t ab2 = Sv[j2].x;
+                        if (x >= (ab2 & 0xFFFFu) && x < (ab2 >> 16)) later = true;
+                    }
+                    if (cov && !later && !((Sv[j].y >> 16) & 1u)) cnt++;
+                }
+            }
+            const uint32_t hb = __ballot_sync(kFull, head);
+            const uint32_t inc = warp_incl_scan(cnt, lane);
+            __syncwarp();                                            // every lane has read its left neighbour's flags
+            if (s < S) {
+                SegFlags[s] = (SegFlags[s] & 0x1Fu) | (head ? 32u : 0u);
+                SegCnt[s] = (uint16_t)cnt;
+                SegOut[s] = (uint16_t)(nspans + __popc(hb & lt));
+                SegCOff[s] = totalC + inc - cnt;
+            }
+            nspans += __popc(hb);
+            totalC += __shfl_sync(kFull, inc, 31);
+            __syncwarp();
+        }
+        if (totalC) {
+            uint32_t pst = 0;
+            if (lane == 0) pool_base = pool_reserve(P, totalC, pst);
+            pst = __shfl_sync(kFull, pst, 0);
+            if (pst) { bail(pst); ps.leave(); return 0; }
+            pool_base = __shfl_sync(kFull, pool_base, 0);
+        }
+        __syncwarp();
+        // pass 3: span records, comment lists (ascending id, sortBy peritext.ts:318), digest
+        uint32_t* pool = P.comment_pool + pool_base;
+#pragma unroll 1
+        for (uint32_t sb = 0; sb < S; sb += 32) {
+            const uint32_t s = sb + lane;
+            const bool head = s < S && (SegFlags[s] & 32u);
+            const uint32_t x = s < S ? (uint32_t)SegStart[s] : 0u;
+            const uint32_t cnt = head ? (uint32_t)SegCnt[s] : 0u, off = head ? SegCOff[s] : 0u;
+            if (nC && __any_sync(kFull, cnt != 0)) {
+                uint32_t filled = 0;
+                for (uint32_t cj = 0; cj < nC; cj++) {
+                    const uint32_t j = CIdx[cj], ab = Sv[j].x, id = Sv[j].z;
+                    const bool cov = cnt != 0 && x >= (ab & 0xFFFFu) && x < (ab >> 16);
+                    if (!__any_sync(kFull, cov)) continue;
+                    bool later = false;
+                    for (uint32_t c2 = cj + 1; c2 < nC; c2++) {
+                        const uint32_t j2 = CIdx[c2];
+                        if (Sv[j2].z != id) continue;
+                        const uint32_t ab2 = Sv[j2].x;
+                        if (x >= (ab2 & 0xFFFFu) && x < (ab2 >> 16)) later = true;
+                    }
+                    if (cov && !later && !((Sv[j].y >> 16) & 1u)) {  // insert in ascending id order (lists are short)
+                        uint32_t y = filled;
+                        while (y > 0 && pool[off + y - 1] > id) { pool[off + y] = pool[off + y - 1]; y--; }
+                        pool[off + y] = id; filled++;
+                    }
+                }
+            }
+            if (head) {
+                const uint32_t jo = SegOut[s];
+                pt_span sp; sp.start = x; sp.flags = (SegFlags[s] & 0xFu) | (cnt << 8); sp.link_attr = SegLink[s];
+                sp.comment_off = cnt ? (uint32_t)(pool_base + off) : 0u;
+                span_out[jo] = sp;
+                for (uint32_t y = 0; y < cnt; y++) digest_add(d0, d1, pt_term_comment(jo, y, pool[off + y]));
+                digest_add(d0, d1, pt_term_span(jo, sp.start, sp.flags, sp.link_attr));
+            }
+        }
+    }
+
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(kFull, d0, o); d1 ^= __shfl_xor_sync(kFull, d1, o); }
+    if (lane == 0) {
+        pt_log_result r;
+        r.status = PT_LOG_OK; r.n_elems = N; r.n_visible = nvis; r.n_spans = nspans;
+        const uint64_t t = pt_term_counts(nvis, nspans);
+        r.digest[0] = d0 + t; r.digest[1] = d1 ^ pt_term_hi(t);
+        *res = r;
+    }
+    ps.leave();
+    return 0;
+}
+
+// Persistent warps: every warp pulls logs (largest first) from the bin's work queue.  Two modes:
+//   free  : each warp takes kWarpGrab logs per atomic and runs on its own;
+//   phased: (prefetch_next bit 2) the CTA takes one log per warp per ROUND and its warps pass the phase barriers together
+//           (consecutive logs of the size-sorted queue are nearly the same size, so a round's warps finish together).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 1) merge_logs_warp_kernel(const BatchParams P) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n_work = P.n_work;
+    const uint32_t slice = P.smem_arena_bytes, base = warp * slice;
+    uint32_t done = 0, deferred = 0;
+    const bool phased = (P.prefetch_next & 4u) != 0;
+    __shared__ uint32_t s_base[2];
+    PhaseSync ps; ps.on = phased ? 1u : 0u; ps.nthreads = WARPS * 32; ps.next = kFirstPhaseBar;
+    uint32_t nextb = 0, par = 0;           // phased: the CTA's next round (held by thread 0)
+    uint32_t w = 0, wend = 0, wn = 0;      // free: this warp's current grab [w, wend) and the next one
+    if (phased) { if (threadIdx.x == 0) nextb = atomicAdd(P.work_counter, (uint32_t)WARPS); }
+    else {
+        if (lane == 0) { w = atomicAdd(P.work_counter, kWarpGrab); wn = atomicAdd(P.work_counter, kWarpGrab); }
+        w = __shfl_sync(kFull, w, 0); wn = __shfl_sync(kFull, wn, 0);
+        wend = min(w + kWarpGrab, n_work);
+    }
+    for (;;) {
+        uint32_t x, xn = 0xFFFFFFFFu;
+        if (phased) {
+            if (threadIdx.x == 0) { s_base[par] = nextb; nextb = atomicAdd(P.work_counter, (uint32_t)WARPS); }
+            asm volatile("barrier.sync 1, %0;" ::"r"((uint32_t)(WARPS * 32)) : "memory");
+            const uint32_t b0 = s_base[par];
+            par ^= 1u;
+            if (b0 >= n_work) break;
+            x = b0 + warp;
+            ps.next = kFirstPhaseBar;
+        } else {
+            if (w >= wend) {
+                w = wn;
+                if (w >= n_work) break;
+                if (lane == 0) wn = atomicAdd(P.work_counter, kWarpGrab);
+                wn = __shfl_sync(kFull, wn, 0);
+                wend = min(w + kWarpGrab, n_work);
+            }
+            x = w++;
+            xn = w < wend ? w : wn;
+        }
+        if (x < n_work) {
+            const uint32_t li = P.order[x];
+            const uint32_t li_next = xn < n_work ? P.order[xn] : 0xFFFFFFFFu;
+            const int rc = warp_merge_one_log(P, li, base, slice, li_next, ps);
+            __syncwarp();
+            if (rc) { if (lane == 0) P.retry_list[atomicAdd(P.retry_count, 1u)] = li; deferred++; } else done++;
+        } else ps.leave();
+    }
+    if (lane == 0) {
+        if (done) atomicAdd(&P.stats[0], (unsigned long long)done);
+        if (deferred) atomicAdd(&P.stats[2], (unsigned long long)deferred);
+    }
+}
+
+}  // namespace ptk

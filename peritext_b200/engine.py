@@ -19,7 +19,7 @@ _lib = None
 
 EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_upload_runs", "pt_compress_runs", "pt_batch_adopt_device", "pt_batch_merge", "pt_batch_sync",
            "pt_batch_download", "pt_batch_download_begin", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count", "pt_batch_stats",
-           "pt_batch_last_merge_ms", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
+           "pt_batch_last_merge_ms", "pt_batch_set_comment_pool", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
 
 
 class EngineError(RuntimeError):
@@ -90,7 +90,8 @@ def compress_runs(batch: PackedBatch, pin=None) -> PackedRuns:
 class _SpansView(ctypes.Structure):
     _fields_ = [("n_logs", ctypes.c_uint32), ("results", ctypes.c_void_p), ("text_off", ctypes.c_void_p),
                 ("span_off", ctypes.c_void_p), ("text", ctypes.c_void_p), ("spans", ctypes.c_void_p),
-                ("comment_pool", ctypes.c_void_p), ("comment_pool_used", ctypes.c_uint64), ("seq", ctypes.c_void_p)]
+                ("comment_pool", ctypes.c_void_p), ("comment_pool_used", ctypes.c_uint64), ("seq", ctypes.c_void_p),
+                ("seq_off", ctypes.c_void_p), ("comment_pool_needed", ctypes.c_uint64)]
 
 
 class _Limits(ctypes.Structure):
@@ -123,6 +124,7 @@ def load_library() -> ctypes.CDLL:
     L.pt_batch_launch_count.argtypes = [vp]; L.pt_batch_launch_count.restype = u64
     L.pt_batch_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 4)]
     L.pt_batch_last_merge_ms.argtypes = [vp]; L.pt_batch_last_merge_ms.restype = ctypes.c_float
+    L.pt_batch_set_comment_pool.argtypes = [vp, u64]
     L.pt_batch_destroy.argtypes = [vp]; L.pt_batch_destroy.restype = None
     L.pt_strerror.argtypes = [ctypes.c_int]; L.pt_strerror.restype = ctypes.c_char_p
     L.pt_last_error.restype = ctypes.c_char_p
@@ -192,7 +194,8 @@ class BatchEngine:
     def stats(self) -> dict:
         out = (ctypes.c_uint64 * 4)()
         _check(self._L.pt_batch_stats(self._h, ctypes.byref(out)), "pt_batch_stats")
-        return {"logs_shared_only": int(out[0]), "logs_spill_path": int(out[1]), "logs_deferred_to_big_bin": int(out[2])}
+        return {"logs_shared_only": int(out[0]), "logs_spill_path": int(out[1]), "logs_deferred_to_big_bin": int(out[2]),
+                "comment_pool_needed": int(out[3])}
 
     def device_results_ptr(self) -> int:
         p = ctypes.c_void_p(); n = ctypes.c_uint32()
@@ -220,22 +223,29 @@ class BatchEngine:
             return a.copy() if copy else a
 
         results = arr(v.results, n, RESULT_DT)
-        text_off = arr(v.text_off, n, np.uint64)
-        span_off = arr(v.span_off, n, np.uint64)
-        n_text = int(text_off[-1]) + 0 if n else 0
-        # capacities: the last log's region ends at its offset + its counts
-        if n:
-            n_text = int(text_off[-1]) + int(results[-1]["n_visible"])
-            n_span = int(span_off[-1]) + int(results[-1]["n_spans"])
-        else:
-            n_span = 0
-        n_seq = (int(text_off[-1]) + int(results[-1]["n_elems"])) if (n and v.seq) else 0
+        text_off = arr(v.text_off, n + 1, np.uint64)      # packed on the device: offsets are the scan of the counts
+        span_off = arr(v.span_off, n + 1, np.uint64)
+        n_text, n_span = int(text_off[-1]), int(span_off[-1])
+        seq_off = arr(v.seq_off, n, np.uint64) if (n and v.seq) else None
+        n_seq = (int(seq_off[-1]) + int(results[-1]["n_elems"])) if seq_off is not None else 0
+        self.comment_pool_needed = int(v.comment_pool_needed)
+        self.comment_pool_used = int(v.comment_pool_used)
         return MergedBatch(results, text_off, span_off, arr(v.text, n_text, np.uint32), arr(v.spans, n_span, SPAN_DT),
                            arr(v.comment_pool, int(v.comment_pool_used), np.uint32),
-                           arr(v.seq, n_seq, np.uint32) if v.seq else None)
+                           arr(v.seq, n_seq, np.uint32) if v.seq else None, seq_off)
+
+    def set_comment_pool(self, entries: int):
+        _check(self._L.pt_batch_set_comment_pool(self._h, int(entries)), "pt_batch_set_comment_pool")
 
     def run(self, batch: PackedBatch) -> MergedBatch:
-        self.upload(batch); self.merge(); return self.download()
+        """upload -> merge -> download.  The comment pool has a default capacity; a log whose comment lists do not fit
+        reports status 4 without consuming pool space and the engine reports the batch's exact demand, so one re-merge
+        with a pool of that size always succeeds (documents with many overlapping comments are valid input)."""
+        self.upload(batch); self.merge(); out = self.download()
+        if len(out.results) and (out.results["status"] == 4).any() and self.comment_pool_needed > self.comment_pool_used:
+            self.set_comment_pool(self.comment_pool_needed + 16)
+            self.merge(); out = self.download()
+        return out
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

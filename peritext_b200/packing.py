@@ -311,9 +311,10 @@ class MergedBatch:
     spans: np.ndarray          # SPAN_DT
     comment_pool: np.ndarray   # u32
     seq: np.ndarray | None = None   # u32 per element (record index | deleted << 31), only with emit_sequence
+    seq_off: np.ndarray | None = None   # u64 [n_logs] offsets into seq (capacity layout); None: same as text_off
 
     def sequence(self, i: int) -> np.ndarray:
-        o = int(self.text_off[i]); return self.seq[o: o + int(self.results[i]["n_elems"])]
+        o = int((self.seq_off if self.seq_off is not None else self.text_off)[i]); return self.seq[o: o + int(self.results[i]["n_elems"])]
 
     def tokens(self, i: int) -> np.ndarray:
         o = int(self.text_off[i]); return self.text[o: o + int(self.results[i]["n_visible"])]

@@ -78,9 +78,13 @@ class ArrivalHistory:
         return t, emits
 
 
-def _slot(b: dict, pos: dict) -> float:
+def _slot(b: dict, pos: dict, hist: "ArrivalHistory | None" = None, t: int | None = None) -> float:
+    """Slot of boundary `b` as seen by a mark op that arrived at time `t`: an element that is unknown, or that is
+    inserted only later at this replica, never matches while walking (src/peritext.ts:236-241)."""
     if b["type"] in ("startOfText", "endOfText") or b["elemId"] not in pos:
-        return INF          # never matches a slot while walking (src/peritext.ts:236-241)
+        return INF
+    if hist is not None and not (b["elemId"] in hist.t_ins and hist.t_ins[b["elemId"]] < t):
+        return INF
     return 2 * pos[b["elemId"]] + (1 if b["type"] == "after" else 0)
 
 
@@ -104,7 +108,7 @@ def derive_patch(op: dict, t: int, pos: dict, hist: ArrivalHistory) -> list[dict
             for (tm, sb, eb, q) in hist.marks:
                 if tm >= t:
                     break
-                qs, qe = _slot(sb, pos), _slot(eb, pos)
+                qs, qe = _slot(sb, pos, hist, tm), _slot(eb, pos, hist, tm)
                 if qe == qs:
                     qe = INF
                 if qs <= s < qe:
@@ -116,7 +120,7 @@ def derive_patch(op: dict, t: int, pos: dict, hist: ArrivalHistory) -> list[dict
         index = sum(1 for e, pe in pos.items() if pe < p and visible(e))
         return [{"path": ["text"], "action": "delete", "index": index, "count": 1}]
     if act in ("addMark", "removeMark"):
-        ps, pe_raw = _slot(op["start"], pos), _slot(op["end"], pos)
+        ps, pe_raw = _slot(op["start"], pos, hist, t), _slot(op["end"], pos, hist, t)
         pe = INF if pe_raw == ps else pe_raw                                   # same slot: start wins, never ends (Q2)
         if ps == INF or ps >= pe:
             return []
@@ -130,7 +134,7 @@ def derive_patch(op: dict, t: int, pos: dict, hist: ArrivalHistory) -> list[dict
         for (tm, sb, eb, q) in hist.marks:
             if tm >= t:
                 break
-            qs, qraw = _slot(sb, pos), _slot(eb, pos)
+            qs, qraw = _slot(sb, pos, hist, tm), _slot(eb, pos, hist, tm)
             qe = INF if qraw == qs else qraw
             earlier.append((qs, qe, q))
             if qs != INF and qs <= qe:

@@ -20,12 +20,14 @@ def weak_doc_first(docs_per_gpu: int, rank: int) -> int:
     return rank * docs_per_gpu
 
 
-def all_gather_results(local_headers, world: int, group=None):
-    """`local_headers`: uint8 tensor [n_logs*32] (device tensor with NCCL, CPU tensor with gloo).  Returns the
-    gathered uint8 tensor [world*n_logs*32]; equal n_logs on every rank (weak sharding)."""
+def all_gather_results(local_headers, world: int, group=None, out=None):
+    """`local_headers`: uint8 tensor [max_logs*32] (device tensor with NCCL, CPU tensor with gloo): the rank's result headers,
+    zero-padded to the largest per-rank log count (a strong split leaves the first `rem` ranks one document more).  Returns
+    the gathered uint8 tensor [world*max_logs*32] (`out` if given); enqueued on the current stream."""
     import torch
     import torch.distributed as dist
-    out = torch.empty(world * local_headers.numel(), dtype=torch.uint8, device=local_headers.device)
+    if out is None:
+        out = torch.empty(world * local_headers.numel(), dtype=torch.uint8, device=local_headers.device)
     dist.all_gather_into_tensor(out, local_headers, group=group)
     return out
 
@@ -33,6 +35,8 @@ def all_gather_results(local_headers, world: int, group=None):
 def convergence_report(headers: np.ndarray, replicas: int) -> dict:
     """`headers`: RESULT_DT array [..., n_logs] with logs ordered doc-major (log = doc*R + r)."""
     h = headers.reshape(-1)
+    if len(h) == 0:
+        return {"all_status_ok": True, "replicas_converged": True, "diverged_docs": []}
     ok = bool((h["status"] == 0).all())
     dig = h["digest"].reshape(-1, replicas, 2)
     same = (dig == dig[:, :1, :]).all(axis=(1, 2))

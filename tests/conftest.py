@@ -24,3 +24,19 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="module", params=["default", "block-only"])
+def engine(request):
+    """The C-ABI engine in its two kernel configurations: default (short logs on the warp-per-log kernel, the rest and its
+    deferrals on the CTA-per-log kernel) and with the warp-per-log bin disabled — results must be identical.  Modules that
+    define their own `engine` fixture run in the default configuration only."""
+    from peritext_b200.engine import BatchEngine
+    if request.param == "block-only":
+        os.environ["PT_WARP"] = "0"
+    else:
+        os.environ.pop("PT_WARP", None)
+    e = BatchEngine(0)
+    yield e
+    e.close()
+    os.environ.pop("PT_WARP", None)

@@ -193,21 +193,23 @@ def merge_log(ins, mk, n_actors, max_ctr):
     for rk, k in enumerate(order):
         mrank[k] = rk
 
-    def slot(btype, ctr, actor, is_start):
+    def slot(btype, ctr, actor, is_start, arrival):
         if btype == 2:                      # startOfText: never matches a slot (peritext.ts:236)
             return None if is_start else 2 * N
         if btype == 3:                      # endOfText: never matches (runs to the end)
             return None if is_start else 2 * N
         j = lookup(ctr, actor)
-        if j == EMPTY:                      # unknown element: the walk never matches it (no throw in the reference)
+        # unknown element, or one that is inserted LATER in this log: the walk at apply time never matches it (no throw
+        # in the reference, peritext.ts:236-241): a missing start is a no-op, a missing end never ends
+        if j == EMPTY or j >= int(arrival):
             return None if is_start else 2 * N
         return 2 * pos[j] + (1 if btype == 1 else 0)
 
     iv = []                                   # per mark op: (a, b) element interval or None
     for k, r in enumerate(mk):
         sb, eb = int(r["bounds"]) & 3, (int(r["bounds"]) >> 2) & 3
-        ps = slot(sb, r["start_ctr"], r["start_actor"], True)
-        pe = slot(eb, r["end_ctr"], r["end_actor"], False)
+        ps = slot(sb, r["start_ctr"], r["start_actor"], True, r["arrival"])
+        pe = slot(eb, r["end_ctr"], r["end_actor"], False, r["arrival"])
         if ps is None:
             iv.append(None); continue
         if pe == ps:                         # same slot: the start branch wins, op never ends (Q2)
@@ -272,7 +274,9 @@ def merge_log(ins, mk, n_actors, max_ctr):
             cover = [j for j in same if iv[j][0] <= e and e2 <= iv[j][1]]
             if not cover:
                 continue
-            wj = max(cover, key=lambda j: mrank[j])
+            # opsToMarks folds comment ops in Set order = ARRIVAL order (peritext.ts:314-322, no opId comparison): the
+            # last-arrived covering op of this id decides (quirk Q4); mark records are stored in arrival order
+            wj = max(cover)
             if (int(mk[wj]["kind"]) & 1) == 0:
                 va, vb = vis_rank[e], vis_rank[e2]
                 if va < vb:

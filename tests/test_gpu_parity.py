@@ -12,14 +12,6 @@ from tests.harness import fuzz_session, generateDocs, load_kats, run_concurrent
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def engine():
-    from peritext_b200.engine import BatchEngine
-    e = BatchEngine(0)
-    yield e
-    e.close()
-
-
 def assert_batch_equal(batch, got, ref):
     assert got.results["status"].tolist() == ref.results["status"].tolist()
     for i in range(batch.n_logs):

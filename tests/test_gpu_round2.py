@@ -1,0 +1,169 @@
+"""GPU parity, round 2: the warp-per-log kernel and its device-side deferrals against the oracle and against the
+CTA-per-log kernel; the reference's arrival-dependent corners (mark boundaries inserted later, quirk Q4); comment-pool
+exhaustion; and the big shapes the round-1 review found untested: one true-shape c5 document (>100K characters, 10K dense
+marks: u32 indices, global-slab spill, every mark phase) and a marks-heavy log of more than 32000 records."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Micromerge as O
+from oracle.packed import replay_packed
+from peritext_b200 import workload
+from peritext_b200.packing import decode_spans, pack_logs
+from tests.harness import generateDocs
+from tests.test_semantic_corners import noncausal_logs, q4_logs
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_equal(batch, got, ref):
+    assert got.results["status"].tolist() == ref.results["status"].tolist()
+    for i in range(batch.n_logs):
+        assert got.canonical(i) == ref.canonical(i), f"log {i}"
+
+
+def test_mark_boundary_inserted_later(engine):
+    cases = noncausal_logs()
+    batch = pack_logs([c[1] for c in cases])
+    got = engine.run(batch)
+    ref, _ = replay_packed(batch)
+    assert_equal(batch, got, ref)
+    for i, c in enumerate(cases):
+        assert decode_spans(batch, got, i) == c[2], c[0]
+
+
+def test_q4_concurrent_add_remove_of_one_comment_id(engine):
+    cases = q4_logs()
+    batch = pack_logs([c[0] for c in cases])
+    got = engine.run(batch)
+    ref, _ = replay_packed(batch)
+    assert_equal(batch, got, ref)
+    for i, c in enumerate(cases):
+        assert decode_spans(batch, got, i) == c[1]
+    assert got.results[0]["digest"].tolist() != got.results[1]["digest"].tolist()      # the reference does not converge here
+
+
+def overlapping_comments_log(k, text_len):
+    """k comments with distinct ids, staggered over one text: ~2k spans x ~k/2 ids each."""
+    docs, _, init = generateDocs(O, "x" * text_len, 1)
+    d = docs[0]
+    chs = [init]
+    for j in range(k):
+        chs.append(d.change([{"path": ["text"], "action": "addMark", "startIndex": j, "endIndex": text_len - k + j + 1,
+                              "markType": "comment", "attrs": {"id": "c%05d" % j}}])["change"])
+    return chs, d.getTextWithFormatting()
+
+
+def test_comment_pool_exhaustion_is_reported_and_one_retry_succeeds(engine):
+    from peritext_b200.engine import BatchEngine
+    big, big_spans = overlapping_comments_log(150, 400)          # needs ~ 150*150 pool entries; default pool = 64*150 + 1024
+    small, small_spans = overlapping_comments_log(3, 10)
+    batch = pack_logs([small, big, small, big, small])
+    # without the retry: the big logs overflow, the small ones are unaffected (no capacity is consumed by a failing log)
+    e = BatchEngine(0)
+    e.upload(batch); e.merge(); out = e.download()
+    assert (out.results["status"] == 4).any() and set(out.results["status"].tolist()) <= {0, 4}
+    assert e.comment_pool_needed > e.comment_pool_used >= 64 * 300 + 1024
+    for i in np.nonzero(out.results["status"] == 0)[0]:
+        assert decode_spans(batch, out, int(i)) == (small_spans if i % 2 == 0 else big_spans)
+    e.close()
+    # BatchEngine.run re-merges once with a pool of exactly the reported size
+    got = engine.run(batch)
+    assert (got.results["status"] == 0).all()
+    assert decode_spans(batch, got, 1) == big_spans and decode_spans(batch, got, 3) == big_spans
+    assert decode_spans(batch, got, 0) == small_spans
+
+
+def run_with(env, batch, force=False):
+    from peritext_b200.engine import BatchEngine
+    old = os.environ.get("PT_WARP")
+    try:
+        os.environ["PT_WARP_FORCE"] = "1" if force else "0"
+        if env is None:
+            os.environ.pop("PT_WARP", None)
+        else:
+            os.environ["PT_WARP"] = env
+        e = BatchEngine(0)
+        e.upload(batch); e.merge(); out = e.download(); st = e.stats()
+        e.close()
+        return out, st
+    finally:
+        os.environ.pop("PT_WARP_FORCE", None)
+        if old is None:
+            os.environ.pop("PT_WARP", None)
+        else:
+            os.environ["PT_WARP"] = old
+
+
+@pytest.mark.parametrize("cfg,n_docs,ops", [("c4", 400, 1000), ("c3", 60, 1000), ("c2", 60, 1500), ("c4", 50, 1900)])
+def test_warp_kernel_equals_block_kernel_equals_oracle(cfg, n_docs, ops):
+    batch = workload.generate(cfg, n_docs=n_docs, ops_per_doc=ops)
+    a, sa = run_with(None, batch)                 # warp-per-log bin (+ deferrals)
+    b, sb = run_with("0", batch)                  # CTA-per-log only
+    c, sc = run_with("2048:4:4608:4", batch, force=True)   # a 4.5 KB slice, host-side estimate skipped: logs run out of
+                                                        # shared memory part-way and are deferred on the device
+    ref, _ = replay_packed(batch, threads=8)
+    for got in (a, b, c):
+        assert_equal(batch, got, ref)
+    assert sb["logs_deferred_to_big_bin"] == 0
+    assert sa["logs_shared_only"] + sa["logs_spill_path"] == batch.n_logs
+    assert sc["logs_deferred_to_big_bin"] > 0
+    if cfg == "c4" and ops == 1000:
+        assert sa["logs_deferred_to_big_bin"] == 0            # the headline shape stays entirely on the warp kernel
+
+
+def test_warp_kernel_dense_surviving_marks_and_comments():
+    # short documents where most mark ops cover visible text (nothing is deleted): the segment-stabbing path with many
+    # survivors, comment lists, and — past the kernel's work bounds — the deferral to the segment-tree kernel
+    logs, spans = [], []
+    for seed, (n_marks, n_comments) in enumerate([(20, 4), (60, 10), (150, 40), (300, 60), (40, 47), (40, 49)]):
+        docs, _, init = generateDocs(O, "The Peritext editor is a rich text CRDT, and this is a sentence.", 1)
+        d = docs[0]
+        rng = np.random.default_rng(seed)
+        chs = [init]
+        L = 64
+        for k in range(n_marks):
+            a = int(rng.integers(0, L - 1)); b = int(rng.integers(a + 1, L + 1))
+            t = ["strong", "em", "link"][k % 3]
+            op = {"path": ["text"], "action": "addMark" if rng.random() < 0.7 else "removeMark", "startIndex": a, "endIndex": b, "markType": t}
+            if t == "link" and op["action"] == "addMark":
+                op["attrs"] = {"url": "%d.com" % (k % 5)}
+            chs.append(d.change([op])["change"])
+        for k in range(n_comments):
+            a = int(rng.integers(0, L - 1)); b = int(rng.integers(a + 1, L + 1))
+            chs.append(d.change([{"path": ["text"], "action": "addMark" if rng.random() < 0.7 else "removeMark", "startIndex": a, "endIndex": b,
+                                  "markType": "comment", "attrs": {"id": "id%02d" % (k % 12)}}])["change"])
+        logs.append(chs); spans.append(d.getTextWithFormatting())
+    batch = pack_logs(logs)
+    a, sa = run_with(None, batch)
+    b, _ = run_with("0", batch)
+    ref, _ = replay_packed(batch)
+    for got in (a, b):
+        assert_equal(batch, got, ref)
+        for i in range(batch.n_logs):
+            assert decode_spans(batch, got, i) == spans[i]
+    assert sa["logs_deferred_to_big_bin"] >= 1 and sa["logs_shared_only"] >= batch.n_logs
+
+
+def test_true_shape_c5_document(engine):
+    """One c5 document at BASELINE.json configs[4]'s real shape: > 100K visible characters, 10K dense overlapping marks
+    (every character covered by ~25 ops): merge_one_log<uint32_t, 1024, false> — u32 indices, id table spilled to the
+    global slab — through every mark phase, all arrays against the oracle (the O(N^2) oracle needs ~30 s for one log)."""
+    batch = workload.generate("c5", n_docs=1)
+    d = batch.desc
+    assert int(d["n_insdel"][0]) > 100000 and int(d["n_mark"][0]) == 10000
+    got = engine.run(batch)
+    ref, _ = replay_packed(batch, first=0, count=1)
+    assert int(ref.results[0]["n_visible"]) >= 100000
+    assert got.canonical(0) == ref.canonical(0)
+    assert got.results[1]["status"] == 0 and got.results[0]["digest"].tolist() == got.results[1]["digest"].tolist()
+
+
+def test_marks_heavy_log_above_32000_records(engine):
+    # c3 shape (10 % mark ops incl. comments) at 40K ops per document: u32 indices with every mark phase
+    batch = workload.generate("c3", n_docs=1, ops_per_doc=40000)
+    assert int(batch.desc["n_insdel"][0]) > 32000 and int(batch.desc["n_mark"][0]) > 3000
+    got = engine.run(batch)
+    ref, _ = replay_packed(batch, threads=2)
+    assert_equal(batch, got, ref)

@@ -66,3 +66,50 @@ def test_shard_range_is_a_partition():
             f, c = shard_range(n, r, w)
             seen += list(range(f, f + c))
         assert seen == list(range(n))
+
+
+def _strong_worker(rank, world, port, n_docs_total, q):
+    """bench.py's N > 1 layout: a fixed document set split with shard_range (uneven: 5 docs over 2 ranks), headers padded to
+    the largest per-rank count, gathered into a caller-provided tensor."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.packed import replay_packed
+    from peritext_b200 import sharding, workload
+    first, count = sharding.shard_range(n_docs_total, rank, world)
+    batch = workload.generate("c4", n_docs=count, ops_per_doc=300, doc_first=first, threads=1)
+    R = batch.meta["replicas"]
+    counts = [sharding.shard_range(n_docs_total, r, world)[1] * R for r in range(world)]
+    merged, _ = replay_packed(batch)
+    stage = torch.zeros(max(counts) * 32, dtype=torch.uint8)
+    stage[: batch.n_logs * 32] = torch.from_numpy(merged.results.view(np.uint8).reshape(-1).copy())
+    out = torch.empty(world * max(counts) * 32, dtype=torch.uint8)
+    sharding.all_gather_results(stage, world, out=out)
+    allh = sharding.headers_from_bytes(out.numpy()).reshape(world, max(counts))
+    reps = [sharding.convergence_report(allh[r, : counts[r]], R) for r in range(world)]
+    vis = [allh[r, : counts[r]]["n_visible"].tolist() for r in range(world)]
+    q.put((rank, counts, vis, reps))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_strong_split_with_uneven_shards():
+    world, n_docs = 2, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_strong_worker, args=(r, world, port, n_docs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0][1] == [9, 6] and out[0][2] == out[1][2]
+    from oracle.packed import replay_packed
+    from peritext_b200 import workload
+    whole = workload.generate("c4", n_docs=n_docs, ops_per_doc=300, threads=1)
+    ref, _ = replay_packed(whole)
+    assert out[0][2][0] + out[0][2][1] == ref.results["n_visible"].tolist()      # the shards concatenate to the whole job
+    for _, _, _, reps in out:
+        assert all(r["all_status_ok"] and r["replicas_converged"] for r in reps)
