@@ -248,6 +248,7 @@ struct pt_batch {
     std::vector<uint64_t> h_text_off, h_span_off;
     std::vector<uint32_t> h_order;
     uint32_t bin_first[kNumBins + 1] = {0};
+    uint32_t warp_compact = 0;              // bin 0: the first warp_compact logs use the compact id table
     size_t bin_slab[kNumBins] = {0};
     size_t retry_slab = 0;
     // device
@@ -316,6 +317,7 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
     b->h_desc.assign(ops->logs, ops->logs + ops->n_logs);
     b->h_text_off.resize(b->n_logs); b->h_span_off.resize(b->n_logs);
     uint64_t to = 0, so = 0, ncomment_bound = 0;
+    uint32_t n_compact = 0;
     std::vector<uint32_t> bins[kNumBins];
     for (int k = 0; k < kNumBins; k++) b->bin_slab[k] = 0;
     for (uint32_t i = 0; i < b->n_logs; i++) {
@@ -343,6 +345,10 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
             const uint64_t idbytes = (R_ >= 3 && R_ <= 30 && n_ <= 2046) ? 2ull * L.max_ctr + 512 : 2 * KS;
             if (g_warp_force || idbytes + n_ / 2 + 16 * n_ / 3 + 1024 <= kBins[0].smem) bin = 0;
         }
+        if (bin == 0) {   // bin 0 is launched twice: compact id table (>= 3 actors) / direct id table
+            const uint64_t R_ = L.n_actors ? L.n_actors : 1;
+            if (R_ >= 3 && R_ <= 30 && L.n_insdel <= 2046) n_compact++;
+        }
         bins[bin].push_back(i);
         if (KS > 0x7FFFFFFFull) { g_last_error = "max_ctr * n_actors too large; re-rank counters densely on the host"; return PT_ERR_INVALID; }
         b->bin_slab[bin] = std::max(b->bin_slab[bin], arena_worst_bytes(L.n_insdel, L.n_mark, KS));
@@ -353,11 +359,14 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
     for (int k = 0; k < kNumBins; k++) {
         b->bin_first[k] = (uint32_t)b->h_order.size();
         auto& v = bins[k];
+        auto is_compact = [&](uint32_t x) { const pt_log_desc& D = b->h_desc[x]; const uint32_t R_ = D.n_actors ? D.n_actors : 1; return R_ >= 3 && R_ <= 30 && D.n_insdel <= 2046; };
         std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) {
+            if (k == 0) { const bool cx = is_compact(x), cy = is_compact(y); if (cx != cy) return cx; }   // compact-table logs first
             return (uint64_t)b->h_desc[x].n_insdel + b->h_desc[x].n_mark > (uint64_t)b->h_desc[y].n_insdel + b->h_desc[y].n_mark; });
         b->h_order.insert(b->h_order.end(), v.begin(), v.end());
     }
     b->bin_first[kNumBins] = (uint32_t)b->h_order.size();
+    b->warp_compact = n_compact;
     return PT_OK;
 }
 
@@ -424,26 +433,33 @@ int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P, bool retry) {
     b->launches++;
     return PT_OK;
 }
-template <int WARPS>
-int launch_warp_bin_t(pt_batch* b, ptk::BatchParams P) {
+template <int WARPS, bool COMPACT>
+int launch_warp_range(pt_batch* b, ptk::BatchParams P, uint32_t first, uint32_t cnt, uint32_t counter_slot) {
+    if (!cnt) return PT_OK;
     const BinCfg& cfg = kBins[0];
-    const uint32_t cnt = b->bin_first[1] - b->bin_first[0];
     const uint32_t per_cta = WARPS * ptk::kWarpGrab;
     const uint32_t grid = (uint32_t)std::min<size_t>((cnt + per_cta - 1) / per_cta, (size_t)b->num_sms * cfg.ctas_per_sm);
     uint32_t* counters = (uint32_t*)((char*)b->d_counters.p + 128);
     uint32_t* lists = (uint32_t*)b->d_retry.p;
-    P.order = (const uint32_t*)b->d_order.p + b->bin_first[0]; P.n_work = cnt; P.n_work_dev = nullptr;
-    P.work_counter = counters + 0;
+    P.order = (const uint32_t*)b->d_order.p + b->bin_first[0] + first; P.n_work = cnt; P.n_work_dev = nullptr;
+    P.work_counter = counters + counter_slot;
     P.slab_bytes = 0;
-    P.retry_list = lists + (size_t)1 * b->n_logs;
+    P.retry_list = lists + (size_t)1 * b->n_logs;        // deferrals go to the first CTA-per-log bin
     P.retry_count = counters + 2 * kNumBins + 1;
     P.smem_arena_bytes = cfg.smem;                       // per warp
     const int smem = (int)(cfg.smem * WARPS);
-    PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_warp_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ptk::merge_logs_warp_kernel<WARPS><<<grid, WARPS * 32, smem, b->stream>>>(P);
+    PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_warp_kernel<WARPS, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ptk::merge_logs_warp_kernel<WARPS, COMPACT><<<grid, WARPS * 32, smem, b->stream>>>(P);
     PT_CUDA(cudaGetLastError());
     b->launches++;
     return PT_OK;
+}
+template <int WARPS>
+int launch_warp_bin_t(pt_batch* b, const ptk::BatchParams& P) {
+    const uint32_t cnt = b->bin_first[1] - b->bin_first[0];
+    int rc = launch_warp_range<WARPS, true>(b, P, 0, b->warp_compact, 0);
+    if (rc) return rc;
+    return launch_warp_range<WARPS, false>(b, P, b->warp_compact, cnt - b->warp_compact, 3 * kNumBins);
 }
 int launch_bin(pt_batch* b, int k, const ptk::BatchParams& P, bool retry) {
     if (!retry && b->bin_first[k + 1] == b->bin_first[k]) return PT_OK;
@@ -615,7 +631,8 @@ static int enqueue_merge(pt_batch* b) {
     P.slab = (char*)b->d_slab.p;
     P.seq = (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) ? (uint32_t*)b->d_seq.p : nullptr;
     P.stats = (unsigned long long*)b->d_counters.p;
-    { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 0u; }   // CTA bins: 1 = next log -> L2; warp bin: bit0 marks, bit1 next log
+    { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 0u; }
+    { const char* e = getenv("PT_WARP_FLAGS"); P.warp_flags = e ? (uint32_t)atoi(e) : 4u; }   // default: phase-aligned warps, no L2 prefetch
     { const char* e = getenv("PT_TMA"); P.use_tma = e ? (uint32_t)atoi(e) : 1u; }
     int rc;
     // ascending bins; a log whose working set does not fit bin k's shared memory is deferred (on the device) to bin k+1;

@@ -51,7 +51,8 @@ struct BatchParams {
     uint32_t* retry_list;                 // non-null: logs that do not fit this bin's shared memory are deferred here
     uint32_t* retry_count;
     const uint32_t* n_work_dev;           // non-null: number of work items is read from device memory (retry launch)
-    uint32_t prefetch_next;               // prefetch the next log's records into L2 while working on the current one
+    uint32_t prefetch_next;               // CTA-per-log kernel: prefetch the next log's records into L2 while working on the current one
+    uint32_t warp_flags;                  // warp-per-log kernel: bit0 prefetch this log's marks, bit1 the next log's records, bit2 phase-aligned warps
     uint32_t use_tma;                     // stage the record stream through shared memory with cp.async.bulk (shared-only path)
     uint32_t* seq;                        // optional: element sequence output (record index | deleted << 31), text offsets
 };

@@ -33,13 +33,14 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
 
 // per-warp bump allocator over the warp's slice of dynamic shared memory (offsets from the __shared__ symbol: LDS/STS)
 struct WArena {
-    uint32_t base, used, cap; bool overflow;
+    uint32_t base, used, cap;
+    // bump; the caller checks fits() once per group of allocations, BEFORE touching any of them
     template <class T> __device__ __forceinline__ T* alloc(uint32_t count) {
-        const uint32_t bytes = (uint32_t)((count * sizeof(T) + 15u) & ~15u);
-        const uint32_t off = used; used += bytes;
-        if (used > cap) { overflow = true; used = off; return reinterpret_cast<T*>(ptk_smem + base); }
+        const uint32_t off = used;
+        used += (uint32_t)((count * sizeof(T) + 15u) & ~15u);
         return reinterpret_cast<T*>(ptk_smem + base + off);
     }
+    __device__ __forceinline__ bool fits() const { return used <= cap; }
 };
 
 // Phase alignment of the warps of one CTA (optional).  The kernel's code is far larger than the instruction caches
@@ -75,8 +76,9 @@ __device__ __forceinline__ void wfill(T* p, uint32_t count, T v, uint32_t lane) 
     for (uint32_t i = lane; i < nvec; i += 32) d[i] = q;
 }
 
-// returns 0: done (result header written), 1: defer to the block kernel
-__device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const uint32_t slice_base, const uint32_t slice_bytes, const uint32_t li_next, PhaseSync ps) {
+// returns 0: done (result header written), 1: defer to the block kernel.  COMPACT selects the id-table form (below).
+template <bool COMPACT>
+__device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const uint32_t slice_base, const uint32_t slice_bytes, const uint32_t li_next, PhaseSync ps) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt = (1u << lane) - 1u;
 
@@ -94,13 +96,13 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
     pt_span* span_out = P.spans + P.span_off[li];
     pt_log_result* res = P.results + li;
 
-    if ((P.prefetch_next & 1u) && m) {       // this log's mark records are needed late: pull them into L2 now
+    if ((P.warp_flags & 1u) && m) {       // this log's mark records are needed late: pull them into L2 now
         const char* p0 = reinterpret_cast<const char*>(mk);
         const uint32_t lines = (m * (uint32_t)sizeof(pt_mark_rec) + 127u) >> 7;
         for (uint32_t l = lane; l < lines; l += 32) prefetch_l2(p0 + ((size_t)l << 7));
     }
 
-    WArena A; A.base = slice_base; A.used = 0; A.cap = slice_bytes; A.overflow = false;
+    WArena A; A.base = slice_base; A.used = 0; A.cap = slice_bytes;
     uint32_t st = 0;                                           // lane-local status, max-reduced at the checkpoints
     auto keyOf = [&](uint32_t ctr, uint32_t actor) -> uint32_t { return (ctr - 1u) * R + actor; };
     auto badId = [&](uint32_t ctr, uint32_t actor) -> bool { return ctr - 1u >= C || actor >= R; };
@@ -113,25 +115,23 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
     //          bounds the number of resident warps.  T[ctr-1] = actor:5 | index:11 of ONE insert with that counter; the few
     //          inserts that share a counter with an earlier one (concurrent edits) go to a small open-addressing overflow
     //          table OV (key:16 | index:16, linear probing).  More than kOvMax of those: the log is deferred.
-    const bool compact = R >= 3u && R <= 30u && n <= 2046u;
+    constexpr bool compact = COMPACT;
+    if (compact && !(R >= 3u && R <= 30u && n <= 2046u)) { ps.leave(); return 1; }     // (the host only sends such logs to this launch)
     constexpr uint32_t kOvSlots = 128, kOvMax = 96, kOvEmpty = 0xFFFFFFFFu;
     const uint32_t NWr = (n + 31) / 32 + 1;                    // bit words over record indices (+1 zero pad word)
-    uint16_t* T = A.alloc<uint16_t>(compact ? C : KS);
+    // layout: the arrays at FIXED offsets first (their addresses are one add away from the slice base)
     uint32_t* OV = A.alloc<uint32_t>(compact ? kOvSlots : 0u);
-    uint32_t* InsBits = A.alloc<uint32_t>(NWr);
-    uint32_t* HeadBits = A.alloc<uint32_t>(NWr);               // first: chain-link bits; after C: run heads
-    uint32_t* VisBits = A.alloc<uint32_t>(NWr);
-    uint16_t* HeadPre = A.alloc<uint16_t>(NWr);
-    uint16_t* VisPre = A.alloc<uint16_t>(NWr);
+    // per 32-record word: x = insert bits, y = chain-link bits (after C: run-head bits), z = visible bits (after C),
+    // w = run heads before the word | visible elements before the word << 16 (after C)
+    uint4* WI = A.alloc<uint4>(NWr);
+    uint16_t* T = A.alloc<uint16_t>(compact ? C : KS);
     const uint32_t markC = A.used;
-    uint32_t* OtherBits = A.alloc<uint32_t>(NWr);              // element has a child that is not its log successor (dead after C)
-    uint32_t* DelBits = A.alloc<uint32_t>(NWr);                // tombstones (dead after C)
-    if (A.overflow) { ps.leave(); return 1; }
+    uint2* OD = A.alloc<uint2>(NWr);                           // x = element has a child that is not its log successor, y = tombstone (dead after C)
+    if (!A.fits()) { ps.leave(); return 1; }
     wfill<uint16_t>(T, compact ? C : KS, (uint16_t)kNone16, lane);
     if (compact) wfill<uint32_t>(OV, kOvSlots, kOvEmpty, lane);
-    wfill<uint32_t>(OtherBits, NWr, 0u, lane);
-    wfill<uint32_t>(DelBits, NWr, 0u, lane);
-    if (lane == 0) { InsBits[NWr - 1] = 0; HeadBits[NWr - 1] = 0; }
+    wfill<uint32_t>(reinterpret_cast<uint32_t*>(OD), 2 * NWr, 0u, lane);
+    if (lane == 0) WI[NWr - 1] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     auto ovHash = [&](uint32_t key) -> uint32_t { return ((key * 40503u) >> 7) & (kOvSlots - 1u); };
     // index of the insert record with opId (ctr, actor), kNone16 if there is none; the id must be in range (!badId)
@@ -154,14 +154,25 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
     //    A referenced element must have arrived EARLIER in the log (src/micromerge.ts:752 throws otherwise).
     uint32_t nOv = 0;
     {
-        const uint4 zero4 = make_uint4(0, 0, 0, 0xC0000000u);
         uint32_t carryK = 0xFFFFFFFFu;                         // key of the last record of the previous trip if it is an insert
-        uint4 ra = lane < n ? ld_rec(ins + lane) : zero4;
-        uint4 rb = 32 + lane < n ? ld_rec(ins + 32 + lane) : zero4;
+        // records past the end are loaded from a clamped index and ignored (every use is guarded by i < n)
+        const uint32_t nm1 = n ? n - 1u : 0u;
+        uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+        if (n) { ra = ld_rec(ins + min(lane, nm1)); rb = ld_rec(ins + min(32u + lane, nm1)); }
+        // an L2 prefetch stream runs kPfTrips trips (512 B each) ahead of the register loads: DRAM latency under load is
+        // longer than two trips
+        constexpr uint32_t kPfTrips = 8;
+        const char* insb = reinterpret_cast<const char*>(ins);
+        const uint32_t insBytes = n * 16u;
+        if (lane * 128u + 1024u < insBytes) prefetch_l2(insb + 1024u + lane * 128u);          // trips 2 .. 9
+        const char* pfp = insb + (kPfTrips + 2u) * 512u + lane * 128u;                      // lanes 0..3: the 4 lines of a trip
+        uint32_t pfo = (kPfTrips + 2u) * 512u + lane * 128u + (lane < 4u ? 0u : 0x40000000u);
 #pragma unroll 1
         for (uint32_t base = 0; base < n; base += 32) {
             const uint32_t i = base + lane;
-            const uint4 rc = base + 64 + lane < n ? ld_rec(ins + base + 64 + lane) : zero4;
+            if (pfo < insBytes) prefetch_l2(pfp);
+            pfp += 512; pfo += 512;
+            const uint4 rc = ld_rec(ins + min(i + 64u, nm1));
             const uint4 r = ra;
             const uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16, kind = r.w >> 30;
             bool isIns = false, valid = false, toOv = false, wrote = false;
@@ -195,7 +206,7 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
             bool cand = isIns && refOk && rkey == prevK;           // typing-chain link: the reference element is record i-1
             if (cand && rkey >= key) { fail(PT_LOG_CYCLE); cand = false; }
             const uint32_t insW = __ballot_sync(kFull, isIns), candW = __ballot_sync(kFull, cand);
-            if (lane == 0) { InsBits[base >> 5] = insW; HeadBits[base >> 5] = candW; }
+            if (lane == 0) *reinterpret_cast<uint2*>(&WI[base >> 5]) = make_uint2(insW, candW);
             __syncwarp();                                          // the trip's ids are in T
             if (!compact) {
                 if (isIns && T[key] != (uint16_t)i) fail(PT_LOG_BAD_OPID);   // two inserts with one opId (same trip)
@@ -224,7 +235,7 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
                     const uint32_t j = refOk ? lookup(ref_ctr, ref_actor) : kNone16;
                     if (j == kNone16 || j >= i) fail(PT_LOG_ELEM_NOT_FOUND);           // must have arrived earlier
                     else if (isIns && rkey >= key) fail(PT_LOG_CYCLE);
-                    else atomicOr(&(isIns ? OtherBits : DelBits)[j >> 5], 1u << (j & 31));   // deletes: OR, idempotent (micromerge.ts:689)
+                    else atomicOr(reinterpret_cast<uint32_t*>(&OD[j >> 5]) + (isIns ? 0u : 1u), 1u << (j & 31));   // deletes: OR, idempotent (micromerge.ts:689)
                 }
             }
             ra = rb; rb = rc;
@@ -243,7 +254,7 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
         for (uint32_t wb = 0; wb < NWr; wb += 32) {
             const uint32_t w = wb + lane;
             uint32_t insW = 0, candW = 0, otherW = 0, delW = 0;
-            if (w < NWr) { insW = InsBits[w]; candW = HeadBits[w]; otherW = OtherBits[w]; delW = DelBits[w]; }
+            if (w < NWr) { const uint2 ic = *reinterpret_cast<const uint2*>(&WI[w]); const uint2 od = OD[w]; insW = ic.x; candW = ic.y; otherW = od.x; delW = od.y; }
             const uint32_t up = __shfl_up_sync(kFull, otherW, 1);
             const uint32_t prevBit = lane ? (up >> 31) : otherCarry;
             otherCarry = __shfl_sync(kFull, otherW, 31) >> 31;
@@ -251,22 +262,28 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
             const uint32_t vis = insW & ~delW;
             const uint32_t pc = __popc(head) | (__popc(vis) << 16);
             const uint32_t inc = warp_incl_scan(pc, lane), ex = inc - pc, tot = __shfl_sync(kFull, inc, 31);
-            if (w < NWr) { HeadBits[w] = head; VisBits[w] = vis; HeadPre[w] = (uint16_t)(carryH + (ex & 0xFFFFu)); VisPre[w] = (uint16_t)(carryV + (ex >> 16)); }
+            if (w < NWr) WI[w] = make_uint4(insW, head, vis, (carryH + (ex & 0xFFFFu)) | ((carryV + (ex >> 16)) << 16));
             carryH += tot & 0xFFFFu; carryV += tot >> 16;
             N += __reduce_add_sync(kFull, (uint32_t)__popc(insW));
         }
         M = carryH; nvis = carryV;
     }
-    A.used = markC;                                                // release OtherBits / DelBits
+    A.used = markC;                                                // release OD
     __syncwarp();
 
     auto runOf = [&](uint32_t i) -> uint32_t {
-        return (uint32_t)HeadPre[i >> 5] + __popc(HeadBits[i >> 5] & (0xFFFFFFFFu >> (31 - (i & 31)))) - 1u;
+        const uint4 q = WI[i >> 5];
+        return (q.w & 0xFFFFu) + __popc(q.y & (0xFFFFFFFFu >> (31 - (i & 31)))) - 1u;
     };
     auto visBefore = [&](uint32_t i) -> uint32_t {
-        return (uint32_t)VisPre[i >> 5] + __popc(VisBits[i >> 5] & ((1u << (i & 31)) - 1u));
+        const uint4 q = WI[i >> 5];
+        return (q.w >> 16) + __popc(q.z & ((1u << (i & 31)) - 1u));
     };
 
+    if (m) {       // the first 6 trips of mark records (needed in phase G) start their way to L2 now
+        const uint32_t pfb = min(m * 32u, 6u * 1024u);
+        for (uint32_t o = lane * 128u; o < pfb; o += 32u * 128u) prefetch_l2(reinterpret_cast<const char*>(mk) + o);
+    }
     // ---- D: run tree; E: Euler tour + splitter list ranking of the VISIBLE weights ------------------------------------------
     const uint32_t E = 2 * (M + 1), END = E;
     if (E + 1 >= 0xFFFFu) { ps.leave(); return 1; }
@@ -286,7 +303,7 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
         // key bitmap + prefix (ranking of the head keys); dead after the ranking, then the splitter summaries live there
         const uint32_t uBytes = max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)(((nSp + 1) * 4 + 15) & ~15u));
         char* U = A.alloc<char>(uBytes);
-        if (A.overflow) { ps.leave(); return 1; }
+        if (!A.fits()) { ps.leave(); return 1; }
         uint32_t* KBits = reinterpret_cast<uint32_t*>(U);
         uint16_t* KPre = reinterpret_cast<uint16_t*>(U + (((KW + 1) * 4 + 15) & ~15u));
         uint32_t* Sub = reinterpret_cast<uint32_t*>(U);
@@ -295,7 +312,8 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
         for (uint32_t wb = 0; wb < NWr; wb += 32) {                // compact the run heads (one bit word per lane)
             const uint32_t w = wb + lane;
             if (w < NWr) {
-                uint32_t hb = HeadBits[w], rid = HeadPre[w];
+                const uint4 q = WI[w];
+                uint32_t hb = q.y, rid = q.w & 0xFFFFu;
                 while (hb) { const uint32_t b = __ffs(hb) - 1; hb &= hb - 1; HV[rid++] = (uint16_t)(w * 32 + b); }
             }
         }
@@ -306,9 +324,10 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
             const uint32_t r = rb + lane;
             if (r < M) {
                 const uint32_t i = HV[r], w = i >> 5, b = i & 31;
-                uint32_t stop = (HeadBits[w] | ~InsBits[w]) & ~(0xFFFFFFFFu >> (31 - b));
+                const uint4 q0 = WI[w];
+                uint32_t stop = (q0.y | ~q0.x) & ~(0xFFFFFFFFu >> (31 - b));
                 uint32_t ww = w;
-                while (!stop) { ww++; stop = HeadBits[ww] | ~InsBits[ww]; }      // pad word: InsBits == 0 -> stops
+                while (!stop) { ww++; const uint2 q1 = *reinterpret_cast<const uint2*>(&WI[ww]); stop = q1.y | ~q1.x; }   // pad word: insert bits == 0 -> stops
                 const uint32_t end = ww * 32 + (__ffs(stop) - 1);
                 const uint4 rec = ld_rec(ins + i);
                 const uint32_t key = keyOf(rec.x, rec.z & 0xFFFFu);
@@ -424,26 +443,36 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
     }
     A.used = markD;                                                // release the run-tree temporaries
     ps.pass();                                                     // (4) sequence ranked
-    auto visOf = [&](uint32_t i) -> uint32_t { return ((uint32_t)VisBase[runOf(i)] + visBefore(i)) & 0xFFFFu; };
-    auto isVis = [&](uint32_t i) -> bool { return (VisBits[i >> 5] >> (i & 31)) & 1u; };
 
-    // ---- F: text out (visible index = prefix count of non-deleted elements, micromerge.ts:747-750) -------------------------
+    // ---- F: per-element visible rank table + text out (visible index = prefix count of non-deleted elements,
+    // micromerge.ts:747-750).  EV[i] = visible elements before insert record i in the sequence | visible << 15: every mark
+    // boundary below is then one table read instead of run / prefix arithmetic.
+    uint16_t* EV = A.alloc<uint16_t>(n + 1);
+    if (!A.fits() || nvis >= 0x8000u) { ps.leave(); return 1; }
     unsigned long long d0 = 0, d1 = 0;
 #pragma unroll 1
     for (uint32_t w = 0; w + 1 < NWr; w++) {
-        const uint32_t vb = VisBits[w];                            // uniform
-        if (!vb) continue;
-        if ((vb >> lane) & 1u) {
+        const uint4 q = WI[w];                                     // uniform: one broadcast LDS.128
+        const uint32_t ib = q.x;
+        if (!ib) continue;
+        const uint32_t hbits = q.y, vbits = q.z, hp = q.w & 0xFFFFu, vp = q.w >> 16;
+        if ((ib >> lane) & 1u) {
             const uint32_t i = w * 32 + lane;
-            const uint32_t tok = PT_PAYLOAD_TOKEN(__ldg(&ins[i].payload));
-            const uint32_t vr = visOf(i);
-            text_out[vr] = tok;
-            digest_add(d0, d1, pt_term_text(vr, tok));
+            const uint32_t run = hp + __popc(hbits & (0xFFFFFFFFu >> (31 - lane))) - 1u;
+            const uint32_t vr = ((uint32_t)VisBase[run] + vp + __popc(vbits & lt)) & 0xFFFFu;
+            const uint32_t isv = (vbits >> lane) & 1u;
+            EV[i] = (uint16_t)(vr | (isv << 15));
+            if (isv) {
+                const uint32_t tok = PT_PAYLOAD_TOKEN(__ldg(&ins[i].payload));
+                text_out[vr] = tok;
+                digest_add(d0, d1, pt_term_text(vr, tok));
+            }
         }
     }
+    __syncwarp();
 
     uint32_t nspans = 0;
-    if ((P.prefetch_next & 2u) && li_next != 0xFFFFFFFFu) {        // the next log's ins/del records -> L2 while this one does its marks
+    if ((P.warp_flags & 2u) && li_next != 0xFFFFFFFFu) {        // the next log's ins/del records -> L2 while this one does its marks
         const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(P.desc + li_next)), q1 = __ldg(reinterpret_cast<const uint4*>(P.desc + li_next) + 1);
         const char* p0 = reinterpret_cast<const char*>(P.insdel + ((unsigned long long)q0.x | ((unsigned long long)q0.y << 32)));
         const uint32_t lines = (q1.x * (uint32_t)sizeof(pt_insdel_rec) + 127u) >> 7;
@@ -458,22 +487,29 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
         const uint32_t KW = (KS + 31) / 32;
         uint32_t* KBits = A.alloc<uint32_t>(KW + 1);               // duplicate mark opIds
         CIdx = A.alloc<uint16_t>(kMaxCommentSurvivors + 32);
-        if (A.overflow) { ps.leave(); return 1; }
+        if (!A.fits()) { ps.leave(); return 1; }
         const uint32_t room = A.cap - A.used, svStart = A.used;
         uint32_t capS = room > 256u ? (room - 256u) / 16u : 0u;
         if (capS > m) capS = m;
         Sv = A.alloc<uint4>(capS + 1);
-        if (A.overflow) { ps.leave(); return 1; }
+        if (!A.fits()) { ps.leave(); return 1; }
         wfill<uint32_t>(KBits, KW + 1, 0u, lane);
         __syncwarp();
         const uint4* mq = reinterpret_cast<const uint4*>(mk);
-        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
-        if (lane < m) { a0 = __ldg(mq + 2 * lane); a1 = __ldg(mq + 2 * lane + 1); }
+        const uint32_t mm1 = m - 1u;                               // m > 0 here; past-the-end lanes load a clamped record, unused
+        uint4 a0 = __ldg(mq + 2 * min(lane, mm1)), a1 = __ldg(mq + 2 * min(lane, mm1) + 1);
+        uint4 c0 = __ldg(mq + 2 * min(lane + 32u, mm1)), c1 = __ldg(mq + 2 * min(lane + 32u, mm1) + 1);
+        const uint32_t mkBytes = m * 32u;
+        const char* mpf = reinterpret_cast<const char*>(mk) + 6u * 1024u + lane * 128u;      // lanes 0..7: the 8 lines of a trip, 4 trips ahead of the loads
+        uint32_t mpo = 6u * 1024u + lane * 128u + (lane < 8u ? 0u : 0x40000000u);
 #pragma unroll 1
         for (uint32_t kb = 0; kb < m; kb += 32) {
             const uint32_t k = kb + lane;
-            uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
-            if (k + 32 < m) { b0 = __ldg(mq + 2 * (size_t)(k + 32)); b1 = __ldg(mq + 2 * (size_t)(k + 32) + 1); }
+            if (mpo < mkBytes) prefetch_l2(mpf);
+            mpf += 1024; mpo += 1024;
+            const uint32_t kn = min(k + 64u, mm1);
+            const uint4 b0 = c0, b1 = c1;
+            c0 = __ldg(mq + 2 * kn); c1 = __ldg(mq + 2 * kn + 1);   // two trips ahead
             // a0 = {ctr, actor|kind<<16|bounds<<24, start_ctr, end_ctr}; a1 = {start_actor|end_actor<<16, attr, arrival, reserved}
             const uint32_t ctr = a0.x, actor = a0.y & 0xFFFFu, kind = (a0.y >> 16) & 0xFFu, bounds = a0.y >> 24;
             const uint32_t start_ctr = a0.z, end_ctr = a0.w, start_actor = a1.x & 0xFFFFu, end_actor = a1.x >> 16, attr = a1.y, arrival = a1.z;
@@ -492,12 +528,13 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
                     if (sb <= PT_BOUND_AFTER && !badId(start_ctr, start_actor)) {
                         const uint32_t js = lookup(start_ctr, start_actor);
                         if (js != kNone16 && js < arrival) {
-                            va = visOf(js) + ((sb && isVis(js)) ? 1u : 0u);
+                            const uint32_t es = EV[js];
+                            va = (es & 0x7FFFu) + (sb & (es >> 15));
                             vb = nvis;
                             if (eb <= PT_BOUND_AFTER && !badId(end_ctr, end_actor)) {
                                 const uint32_t je = lookup(end_ctr, end_actor);
                                 // same slot: the start branch wins and the op never ends (quirk Q2)
-                                if (je != kNone16 && je < arrival && !(je == js && eb == sb)) vb = visOf(je) + ((eb && isVis(je)) ? 1u : 0u);
+                                if (je != kNone16 && je < arrival && !(je == js && eb == sb)) { const uint32_t ee = EV[je]; vb = (ee & 0x7FFFu) + (eb & (ee >> 15)); }
                             }
                             surv = va < vb;
                         }
@@ -541,7 +578,7 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
         const uint32_t BW = nvis / 32 + 1;
         uint32_t* Bnd = A.alloc<uint32_t>(BW + 1);
         uint16_t* BPre = A.alloc<uint16_t>(BW + 1);
-        if (A.overflow) { ps.leave(); return 1; }
+        if (!A.fits()) { ps.leave(); return 1; }
         wfill<uint32_t>(Bnd, BW + 1, 0u, lane);
         __syncwarp();
 #pragma unroll 1
@@ -568,7 +605,7 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
         uint16_t* SegCnt = A.alloc<uint16_t>(S + 1);                 // comment ids of the span starting here
         uint16_t* SegOut = A.alloc<uint16_t>(S + 1);                 // span index
         uint32_t* SegCOff = A.alloc<uint32_t>(S + 1);                // offset of its comment list in the log's pool reservation
-        if (A.overflow) { ps.leave(); return 1; }
+        if (!A.fits()) { ps.leave(); return 1; }
         __syncwarp();
 #pragma unroll 1
         for (uint32_t wb = 0; wb < BW; wb += 32) {
@@ -735,15 +772,17 @@ __device__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const
 
 // Persistent warps: every warp pulls logs (largest first) from the bin's work queue.  Two modes:
 //   free  : each warp takes kWarpGrab logs per atomic and runs on its own;
-//   phased: (prefetch_next bit 2) the CTA takes one log per warp per ROUND and its warps pass the phase barriers together
+//   phased: (warp_flags bit 2, the default) the CTA takes one log per warp per ROUND and its warps pass the phase barriers together
 //           (consecutive logs of the size-sorted queue are nearly the same size, so a round's warps finish together).
-template <int WARPS>
+template <int WARPS, bool COMPACT>
 __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 1) merge_logs_warp_kernel(const BatchParams P) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_work = P.n_work;
-    const uint32_t slice = P.smem_arena_bytes, base = warp * slice;
+    const uint32_t slice = P.smem_arena_bytes;
+    uint32_t base = warp * slice;
+    asm volatile("" : "+r"(base));         // opaque: keep it in a register instead of re-deriving it from threadIdx at every shared-memory access
     uint32_t done = 0, deferred = 0;
-    const bool phased = (P.prefetch_next & 4u) != 0;
+    const bool phased = (P.warp_flags & 4u) != 0;
     __shared__ uint32_t s_base[2];
     PhaseSync ps; ps.on = phased ? 1u : 0u; ps.nthreads = WARPS * 32; ps.next = kFirstPhaseBar;
     uint32_t nextb = 0, par = 0;           // phased: the CTA's next round (held by thread 0)
@@ -778,7 +817,7 @@ __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 
         if (x < n_work) {
             const uint32_t li = P.order[x];
             const uint32_t li_next = xn < n_work ? P.order[xn] : 0xFFFFFFFFu;
-            const int rc = warp_merge_one_log(P, li, base, slice, li_next, ps);
+            const int rc = warp_merge_one_log<COMPACT>(P, li, base, slice, li_next, ps);   // the host put the log in the right launch
             __syncwarp();
             if (rc) { if (lane == 0) P.retry_list[atomicAdd(P.retry_count, 1u)] = li; deferred++; } else done++;
         } else ps.leave();
