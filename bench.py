@@ -130,6 +130,33 @@ def cpu_baseline(config, n_docs_total, ops_per_doc):
             "runs": [round(r) for r in rates]}
 
 
+def ingest_throughput(config, logs=240):
+    """Native wire-format ingest (pt_ingest_parse: JSON Change[] -> packed records + change table), all host threads, on a
+    bounded sample of the workload re-expressed as JSON; checked by merging the ingested batch (same visible text)."""
+    from peritext_b200 import workload
+    from peritext_b200.engine import BatchEngine, pack_logs_native
+    cores = os.cpu_count() or 1
+    R = workload.CONFIGS[config]["replicas"]
+    sample = workload.generate(config, n_docs=max(1, logs // R), ops_per_doc=1000 if config != "c4" else None)
+    texts = [workload.to_change_json(sample, i) for i in range(sample.n_logs)]
+    nbytes = sum(len(t) for t in texts)
+    pack_logs_native(texts[:8])
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        got = pack_logs_native(texts, threads=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    eng = BatchEngine(0)
+    a, b = eng.run(sample), eng.run(got)
+    eng.close()
+    same = bool((a.results["n_visible"] == b.results["n_visible"]).all() and (a.results["n_spans"] == b.results["n_spans"]).all()
+                and a.text.tobytes() == b.text.tobytes() and (b.results["status"] == 0).all())
+    return {"api": "pt_ingest_parse (C-ABI) via engine.pack_logs_native, includes copying the packed arrays to numpy", "threads": cores,
+            "logs": sample.n_logs, "op_records": sample.n_ops, "json_bytes": nbytes, "seconds": best, "mb_per_s": nbytes / best / 1e6,
+            "ops_per_s": sample.n_ops / best, "merge_of_ingested_batch_matches": same}
+
+
 def run_reference(args, rank, world):
     """--impl reference arm: rank 0 only; never loads the engine library."""
     if rank != 0:
@@ -451,6 +478,8 @@ def main():
             line["weak"] = weak
         if extras:
             line["extra_configs"] = extras
+        if world == 1 and not args.no_extras:
+            line["ingest"] = ingest_throughput(args.config)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.config, n_docs_total, args.ops_per_doc)
         print(json.dumps(line))

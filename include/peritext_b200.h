@@ -119,6 +119,40 @@ typedef struct pt_packed_runs {
     uint64_t n_mark_total;
 } pt_packed_runs;
 
+/* ------------------------------------------------------------------------------------------------
+ * Change table (optional): what Micromerge.applyChange checks BEFORE it applies a change
+ * (src/micromerge.ts:499-511): seq == clock[actor] + 1, and every deps[a] <= clock[a] (a missing or
+ * zero clock entry fails).  One pt_change_rec per Change the replica applied, in arrival order; the
+ * admission pre-pass (pt_batch_upload_changes) validates every log on the device and reports the
+ * first rejected change as the log's status instead of throwing mid-batch; such a log is not merged.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_change_rec {   /* 16 B */
+    uint32_t seq;     /* change.seq                                                                */
+    uint16_t actor;   /* change.actor, rank among the log's actors (same ranks as the op records)  */
+    uint16_t n_deps;  /* entries of change.deps                                                    */
+    uint32_t dep_off; /* first pt_dep_rec of the change, relative to the log's dep_off             */
+    uint32_t n_ops;   /* ops of the change that target the log's text list (informational)         */
+} pt_change_rec;
+typedef struct pt_dep_rec {      /* 8 B */
+    uint32_t seq;
+    uint16_t actor;
+    uint16_t reserved;
+} pt_dep_rec;
+typedef struct pt_change_desc {  /* 24 B */
+    uint64_t change_off;
+    uint64_t dep_off;
+    uint32_t n_changes;
+    uint32_t n_deps;
+} pt_change_desc;
+typedef struct pt_change_table {
+    uint32_t n_logs;              /* must equal the uploaded batch's n_logs */
+    const pt_change_desc* logs;
+    const pt_change_rec* changes;
+    uint64_t n_changes_total;
+    const pt_dep_rec* deps;
+    uint64_t n_deps_total;
+} pt_change_table;
+
 /* A host-side batch of logs (SoA). */
 typedef struct pt_packed_ops {
     uint32_t n_logs;
@@ -139,7 +173,13 @@ typedef struct pt_packed_ops {
 #define PT_LOG_BAD_OPID 2u       /* ctr/actor outside the descriptor's bounds, or duplicate opId   */
 #define PT_LOG_BAD_KIND 3u       /* record kind not insert/delete                                  */
 #define PT_LOG_OVERFLOW 4u       /* an engine capacity (comment pool / scratch) was exceeded       */
-#define PT_LOG_CYCLE 5u          /* reference elemId does not causally precede the insert          */
+#define PT_LOG_CYCLE 5u          /* reference elemId does not causally precede the insert (a peer chose a startOp below
+                                    an element it references: the reference would still merge it; this engine's
+                                    closed form needs Lamport counters, src/micromerge.ts:487,511)                */
+#define PT_LOG_SEQ_GAP 6u        /* admission: "Expected sequence number ..." src/micromerge.ts:501-504; n_elems =
+                                    index of the rejected change in the log                                        */
+#define PT_LOG_MISSING_DEP 7u    /* admission: "Missing dependency ..." src/micromerge.ts:505-509; n_elems = index of
+                                    the rejected change                                                            */
 
 /* Per-log result header. 32 B. */
 typedef struct pt_log_result {
@@ -224,6 +264,12 @@ int pt_batch_upload_runs(pt_batch*, const pt_packed_runs* host_runs);
 int pt_compress_runs(const pt_packed_ops* ops, uint64_t* run_off, uint64_t* tok_off, pt_run_rec* runs, uint32_t* tokens,
                      uint64_t* n_runs, uint64_t* n_tokens);
 
+/* Attach the change table of the uploaded batch (host arrays, copied): the next pt_batch_merge first runs the
+ * admission pre-pass on the device; logs with a sequence gap / missing dependency get PT_LOG_SEQ_GAP /
+ * PT_LOG_MISSING_DEP and are skipped by the merge (the reference throws before mutating, src/micromerge.ts:501-509).
+ * Call after pt_batch_upload*; a new upload drops the table. */
+int pt_batch_upload_changes(pt_batch*, const pt_change_table* host_changes);
+
 /* Adopt a batch that is ALREADY RESIDENT in device memory (pointers are device pointers owned by the
  * caller, e.g. torch tensors); only the descriptors are read on the host. */
 int pt_batch_adopt_device(pt_batch*, const pt_packed_ops* host_desc_device_arrays);
@@ -268,6 +314,28 @@ int pt_batch_set_comment_pool(pt_batch*, uint64_t entries);
 float pt_batch_last_merge_ms(pt_batch*);
 
 void pt_batch_destroy(pt_batch*);
+
+/* ------------------------------------------------------------------------------------------------
+ * Native wire-format ingest (host, multithreaded): JSON text of the reference's Change objects
+ * (src/micromerge.ts:60-71; the `queues` of the traces/ files) -> packed batch + change table + string pools.
+ * logs_json[i] = UTF-8 JSON array of the Change objects replica i applied, in arrival order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_ingest pt_ingest;
+#define PT_POOL_VALUES 0        /* multi-character element values, UTF-16LE; token = PT_TOKEN_POOLED | index          */
+#define PT_POOL_LINK_ATTRS 1    /* link attrs as canonical JSON (UTF-8); pt_mark_rec.attr = index                      */
+#define PT_POOL_COMMENT_IDS 2   /* comment ids, UTF-16LE, in rank order (JS string order); pt_mark_rec.attr = rank     */
+#define PT_POOL_COMMENT_ATTRS 3 /* the first-seen attrs object of each comment id as canonical JSON, same order        */
+#define PT_POOL_ACTORS 4        /* actor ids UTF-16LE, rank order per log; per_log_first[i] .. per_log_first[i+1]       */
+#define PT_POOL_COUNTERS 5      /* dense counter rank -> original counter (u64 each) of logs whose counters were
+                                   re-ranked; empty range otherwise; per_log_first as above                            */
+int pt_ingest_create(pt_ingest** out);
+int pt_ingest_parse(pt_ingest*, const char* const* logs_json, const uint64_t* lens, uint32_t n_logs, int threads /* 0 = all cores */);
+/* Views into the parsed batch (valid until the next pt_ingest_parse / pt_ingest_destroy). */
+int pt_ingest_packed(pt_ingest*, pt_packed_ops* ops, pt_change_table* changes);
+int pt_ingest_pool(pt_ingest*, int kind, const uint8_t** data, const uint64_t** offsets /* [count + 1] */, uint64_t* count,
+                   const uint64_t** per_log_first /* may be NULL */);
+const char* pt_ingest_error(pt_ingest*);
+void pt_ingest_destroy(pt_ingest*);
 
 const char* pt_strerror(int status);
 const char* pt_last_error(void); /* thread-local detail string of the last failing call */

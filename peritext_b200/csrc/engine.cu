@@ -233,6 +233,63 @@ __global__ void out_gather_kernel(const pt_log_result* __restrict__ res, uint32_
     }
 }
 
+
+// ---- admission pre-pass: Micromerge.applyChange's causal checks (reference src/micromerge.ts:499-511) for every log -------
+// One warp per log, one lane per change, 32 changes per trip.  The reference keeps clock[actor] = seq of the last applied
+// change; as long as every earlier change of the log was admitted that is the NUMBER of earlier changes by that actor, so
+// each change can be checked independently against per-actor prefix counts (match_any groups inside the trip + running
+// counts in shared memory), and the FIRST failing change — what the reference would throw at — is a min over lanes.
+__global__ void admit_kernel(const pt_change_desc* __restrict__ cd, const pt_change_rec* __restrict__ ch, const pt_dep_rec* __restrict__ dp,
+                             const pt_log_desc* __restrict__ desc, uint32_t n_logs, uint32_t maxR, uint32_t* __restrict__ admit, pt_log_result* __restrict__ results) {
+    extern __shared__ uint32_t adm_smem[];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    uint32_t* cnt = adm_smem + (size_t)wib * 2 * maxR;      // changes admitted so far, per actor
+    uint32_t* cmask = cnt + maxR;                           // lanes of the current trip, per actor
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t li = blockIdx.x * wpb + wib; li < n_logs; li += gridDim.x * wpb) {
+        const pt_change_desc D = cd[li];
+        const uint32_t R = desc[li].n_actors ? desc[li].n_actors : 1u;
+        for (uint32_t a = lane; a < R; a += 32) { cnt[a] = 0; cmask[a] = 0; }
+        __syncwarp();
+        const pt_change_rec* c0 = ch + D.change_off; const pt_dep_rec* d0 = dp + D.dep_off;
+        uint32_t fail_idx = 0xFFFFFFFFu, fail_code = 0;
+        for (uint32_t base = 0; base < D.n_changes; base += 32) {
+            const uint32_t k = base + lane;
+            const bool valid = k < D.n_changes;
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (valid) r = __ldg(reinterpret_cast<const uint4*>(c0 + k));
+            const uint32_t seq = r.x, actor = r.y & 0xFFFFu, n_deps = r.y >> 16, dep_off = r.z;
+            const bool aok = valid && actor < R;
+            const uint32_t a = aok ? actor : (0x10000u + lane);
+            const uint32_t mask = __match_any_sync(0xffffffffu, a);
+            const bool leader = (mask & lt) == 0;
+            if (aok && leader) cmask[actor] = mask;
+            __syncwarp();
+            uint32_t code = 0;
+            if (valid) {
+                if (!aok) code = PT_LOG_BAD_OPID;
+                else if (seq != cnt[actor] + __popc(mask & lt) + 1u) code = PT_LOG_SEQ_GAP;            // src/micromerge.ts:501-504
+                else if (dep_off + n_deps > D.n_deps) code = PT_LOG_BAD_OPID;
+                else for (uint32_t d = 0; d < n_deps; d++) {                                            // src/micromerge.ts:505-509
+                    const pt_dep_rec q = d0[dep_off + d];
+                    const uint32_t have = q.actor < R ? cnt[q.actor] + __popc(cmask[q.actor] & lt) : 0u;
+                    if (have == 0 || have < q.seq) { code = PT_LOG_MISSING_DEP; break; }
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, code != 0);
+            if (bal) { const uint32_t f = __ffs(bal) - 1; fail_idx = base + f; fail_code = __shfl_sync(0xffffffffu, code, f); break; }
+            __syncwarp();
+            if (aok && leader) { cnt[actor] += __popc(mask); cmask[actor] = 0; }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            admit[li] = fail_code;
+            if (fail_code) { pt_log_result r{}; r.status = fail_code; r.n_elems = fail_idx; results[li] = r; }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 struct pt_batch {
@@ -255,6 +312,9 @@ struct pt_batch {
     DevBuf d_runs, d_tokens, d_run_off, d_tok_off;
     DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_slab, d_retry, d_seq;
     DevBuf d_bsum, d_ctoff, d_csoff, d_ctext, d_cspans;   // download path: packed outputs + their offsets ([n_logs + 1])
+    DevBuf d_cdesc, d_changes, d_deps, d_admit;           // admission pre-pass (optional change table)
+    bool have_changes = false;
+    uint32_t adm_maxR = 1;
     const pt_insdel_rec* dp_insdel = nullptr;
     const pt_mark_rec* dp_marks = nullptr;
     // pinned host
@@ -514,7 +574,7 @@ static int upload_common(pt_batch* b, const pt_packed_ops* ops, bool adopt) {
     PT_CUDA(cudaStreamSynchronize(b->stream));            // the staging buffer and the device arrays of the previous batch are reused
     b->have_batch = false; b->merged = false;
     if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
-    b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0; b->dl_begun = false;
+    b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0; b->dl_begun = false; b->have_changes = false;
     int rc = plan_batch(b, ops);
     if (rc) return rc;
     if ((rc = alloc_and_upload_plan(b))) return rc;
@@ -546,7 +606,7 @@ int pt_batch_upload_runs(pt_batch* b, const pt_packed_runs* rr) {
     PT_CUDA(cudaStreamSynchronize(b->stream));            // the staging buffer and the device arrays of the previous batch are reused
     b->have_batch = false; b->merged = false;
     if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
-    b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0; b->dl_begun = false;
+    b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0; b->dl_begun = false; b->have_changes = false;
     pt_packed_ops ops{rr->n_logs, rr->logs, nullptr, rr->n_insdel_total, nullptr, rr->n_mark_total};
     int rc = plan_batch(b, &ops);
     if (rc) return rc;
@@ -619,6 +679,35 @@ int pt_compress_runs(const pt_packed_ops* ops, uint64_t* run_off, uint64_t* tok_
 }
 int pt_batch_adopt_device(pt_batch* b, const pt_packed_ops* ops) { return upload_common(b, ops, true); }
 
+int pt_batch_upload_changes(pt_batch* b, const pt_change_table* t) {
+    if (!b || !t) return PT_ERR_INVALID;
+    if (!b->have_batch) { g_last_error = "pt_batch_upload_changes before pt_batch_upload"; return PT_ERR_STATE; }
+    if (t->n_logs != b->n_logs || (t->n_logs && !t->logs)) { g_last_error = "change table does not match the batch"; return PT_ERR_INVALID; }
+    PT_CUDA(cudaSetDevice(b->device));
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    uint32_t maxR = 1;
+    for (uint32_t i = 0; i < b->n_logs; i++) {
+        const pt_change_desc& D = t->logs[i];
+        if (D.change_off + D.n_changes > t->n_changes_total || D.dep_off + D.n_deps > t->n_deps_total) { g_last_error = "change descriptor out of range"; return PT_ERR_INVALID; }
+        maxR = std::max<uint32_t>(maxR, b->h_desc[i].n_actors);
+    }
+    if ((size_t)2 * maxR * 4 > 200 * 1024) { g_last_error = "more than 25600 actors in one log: not supported by the admission pre-pass"; return PT_ERR_INVALID; }
+    int rc;
+    const size_t n = b->n_logs;
+    if ((rc = b->d_cdesc.reserve(std::max<size_t>(1, n) * sizeof(pt_change_desc)))) return rc;
+    if ((rc = b->d_changes.reserve(std::max<uint64_t>(1, t->n_changes_total) * sizeof(pt_change_rec)))) return rc;
+    if ((rc = b->d_deps.reserve(std::max<uint64_t>(1, t->n_deps_total) * sizeof(pt_dep_rec)))) return rc;
+    if ((rc = b->d_admit.reserve(std::max<size_t>(1, n) * 4))) return rc;
+    if (n) PT_CUDA(cudaMemcpyAsync(b->d_cdesc.p, t->logs, n * sizeof(pt_change_desc), cudaMemcpyHostToDevice, b->stream));
+    if (t->n_changes_total) PT_CUDA(cudaMemcpyAsync(b->d_changes.p, t->changes, t->n_changes_total * sizeof(pt_change_rec), cudaMemcpyHostToDevice, b->stream));
+    if (t->n_deps_total) PT_CUDA(cudaMemcpyAsync(b->d_deps.p, t->deps, t->n_deps_total * sizeof(pt_dep_rec), cudaMemcpyHostToDevice, b->stream));
+    PT_CUDA(cudaStreamSynchronize(b->stream));            // the caller's arrays may be freed on return
+    b->adm_maxR = maxR; b->have_changes = true;
+    if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }   // the launch sequence changes
+    b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0;
+    return PT_OK;
+}
+
 static int enqueue_merge(pt_batch* b) {
     PT_CUDA(cudaMemsetAsync(b->d_counters.p, 0, 256, b->stream));   // stats, pool cursor and queue counters in one shot
     ptk::BatchParams P{};
@@ -631,6 +720,20 @@ static int enqueue_merge(pt_batch* b) {
     P.slab = (char*)b->d_slab.p;
     P.seq = (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) ? (uint32_t*)b->d_seq.p : nullptr;
     P.stats = (unsigned long long*)b->d_counters.p;
+    P.admit = nullptr;
+    if (b->have_changes && b->n_logs) {
+        // admission pre-pass: 4 warps per CTA while the per-actor tables fit, else one warp with up to 200 KB
+        const size_t per_warp = (size_t)2 * b->adm_maxR * 4;
+        const uint32_t wpb = per_warp * 4 <= 48 * 1024 ? 4u : 1u;
+        const size_t smem = per_warp * wpb;
+        if (smem > 48 * 1024) PT_CUDA(cudaFuncSetAttribute(admit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)b->n_logs + wpb - 1) / wpb, (uint64_t)b->num_sms * 16);
+        admit_kernel<<<grid, wpb * 32, smem, b->stream>>>((const pt_change_desc*)b->d_cdesc.p, (const pt_change_rec*)b->d_changes.p, (const pt_dep_rec*)b->d_deps.p,
+                                                       (const pt_log_desc*)b->d_desc.p, b->n_logs, b->adm_maxR, (uint32_t*)b->d_admit.p, (pt_log_result*)b->d_results.p);
+        PT_CUDA(cudaGetLastError());
+        b->launches++;
+        P.admit = (const uint32_t*)b->d_admit.p;
+    }
     { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 0u; }
     { const char* e = getenv("PT_WARP_FLAGS"); P.warp_flags = e ? (uint32_t)atoi(e) : 4u; }   // default: phase-aligned warps, no L2 prefetch
     { const char* e = getenv("PT_TMA"); P.use_tma = e ? (uint32_t)atoi(e) : 1u; }
@@ -834,7 +937,8 @@ void pt_batch_destroy(pt_batch* b) {
     cudaStreamSynchronize(b->stream);
     for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
                       &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_slab, &b->d_retry, &b->d_seq,
-                      &b->d_runs, &b->d_tokens, &b->d_run_off, &b->d_tok_off, &b->d_bsum, &b->d_ctoff, &b->d_csoff, &b->d_ctext, &b->d_cspans}) d->release();
+                      &b->d_runs, &b->d_tokens, &b->d_run_off, &b->d_tok_off, &b->d_bsum, &b->d_ctoff, &b->d_csoff, &b->d_ctext, &b->d_cspans,
+                      &b->d_cdesc, &b->d_changes, &b->d_deps, &b->d_admit}) d->release();
     for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc, &b->h_seq, &b->h_ctoff, &b->h_csoff}) h->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);

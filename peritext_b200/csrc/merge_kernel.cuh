@@ -55,6 +55,7 @@ struct BatchParams {
     uint32_t warp_flags;                  // warp-per-log kernel: bit0 prefetch this log's marks, bit1 the next log's records, bit2 phase-aligned warps
     uint32_t use_tma;                     // stage the record stream through shared memory with cp.async.bulk (shared-only path)
     uint32_t* seq;                        // optional: element sequence output (record index | deleted << 31), text offsets
+    const uint32_t* admit;                // optional: per-log admission status (pre-pass); non-zero: the log is not merged
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1034,6 +1035,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : 
             for (uint32_t l = threadIdx.x; l < lines; l += BLOCK) prefetch_l2(p0 + ((size_t)l << 7));
         }
         const uint32_t li = P.order[w];
+        if (P.admit && P.admit[li]) continue;      // rejected by the admission pre-pass (its status is already in the result header)
         const pt_log_desc& L = P.desc[li];
         const bool small = L.n_insdel < 32000u && L.n_mark < 32000u;
         // optimistic: everything in shared memory (LDS/STS); restart with the spill-capable variant if it does not fit

@@ -816,6 +816,7 @@ __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 
         }
         if (x < n_work) {
             const uint32_t li = P.order[x];
+            if (P.admit && P.admit[li]) { ps.leave(); continue; }      // rejected by the admission pre-pass
             const uint32_t li_next = xn < n_work ? P.order[xn] : 0xFFFFFFFFu;
             const int rc = warp_merge_one_log<COMPACT>(P, li, base, slice, li_next, ps);   // the host put the log in the right launch
             __syncwarp();

@@ -11,13 +11,14 @@ import os
 
 import numpy as np
 
-from .packing import (RESULT_DT, SPAN_DT, MergedBatch, PackedBatch)
+from .packing import (CDESC_DT, CHANGE_DT, DEP_DT, DESC_DT, INSDEL_DT, MARK_DT, RESULT_DT, SPAN_DT, ChangeTable, MergedBatch, PackedBatch)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libperitext_b200.so")
 _lib = None
 
-EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_upload_runs", "pt_compress_runs", "pt_batch_adopt_device", "pt_batch_merge", "pt_batch_sync",
+EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_upload_runs", "pt_compress_runs", "pt_batch_adopt_device", "pt_batch_upload_changes",
+           "pt_ingest_create", "pt_ingest_parse", "pt_ingest_packed", "pt_ingest_pool", "pt_ingest_error", "pt_ingest_destroy", "pt_batch_merge", "pt_batch_sync",
            "pt_batch_download", "pt_batch_download_begin", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count", "pt_batch_stats",
            "pt_batch_last_merge_ms", "pt_batch_set_comment_pool", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
 
@@ -87,6 +88,11 @@ def compress_runs(batch: PackedBatch, pin=None) -> PackedRuns:
     return PackedRuns(desc, alloc(run_off), alloc(tok_off), runs[: nr.value], tokens[: nt.value], alloc(marks) if pin else marks, len(insdel))
 
 
+class _ChangeTable(ctypes.Structure):
+    _fields_ = [("n_logs", ctypes.c_uint32), ("logs", ctypes.c_void_p), ("changes", ctypes.c_void_p), ("n_changes_total", ctypes.c_uint64),
+                ("deps", ctypes.c_void_p), ("n_deps_total", ctypes.c_uint64)]
+
+
 class _SpansView(ctypes.Structure):
     _fields_ = [("n_logs", ctypes.c_uint32), ("results", ctypes.c_void_p), ("text_off", ctypes.c_void_p),
                 ("span_off", ctypes.c_void_p), ("text", ctypes.c_void_p), ("spans", ctypes.c_void_p),
@@ -115,6 +121,13 @@ def load_library() -> ctypes.CDLL:
     L.pt_batch_adopt_device.argtypes = [vp, vp]
     L.pt_batch_upload_runs.argtypes = [vp, vp]
     L.pt_compress_runs.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.pt_batch_upload_changes.argtypes = [vp, vp]
+    L.pt_ingest_create.argtypes = [ctypes.POINTER(vp)]
+    L.pt_ingest_parse.argtypes = [vp, vp, vp, u32, ctypes.c_int]
+    L.pt_ingest_packed.argtypes = [vp, vp, vp]
+    L.pt_ingest_pool.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u64), ctypes.POINTER(vp)]
+    L.pt_ingest_error.argtypes = [vp]; L.pt_ingest_error.restype = ctypes.c_char_p
+    L.pt_ingest_destroy.argtypes = [vp]; L.pt_ingest_destroy.restype = None
     L.pt_batch_merge.argtypes = [vp]
     L.pt_batch_sync.argtypes = [vp]
     L.pt_batch_download.argtypes = [vp, vp]
@@ -161,6 +174,13 @@ class BatchEngine:
         ops = self._ops_struct(desc, insdel.ctypes.data, len(insdel), marks.ctypes.data, len(marks))
         _check(self._L.pt_batch_upload(self._h, ctypes.byref(ops)), "pt_batch_upload")
         self.n_logs = len(desc)
+
+    def upload_changes(self, table: ChangeTable):
+        """Attach the batch's change table: the next merge runs the admission pre-pass (seq / deps checks of
+        Micromerge.applyChange, reference src/micromerge.ts:501-509) and rejected logs report status 6 / 7."""
+        d, c, p = np.ascontiguousarray(table.desc), np.ascontiguousarray(table.changes), np.ascontiguousarray(table.deps)
+        t = _ChangeTable(len(d), d.ctypes.data, c.ctypes.data if len(c) else 0, len(c), p.ctypes.data if len(p) else 0, len(p))
+        _check(self._L.pt_batch_upload_changes(self._h, ctypes.byref(t)), "pt_batch_upload_changes")
 
     def upload_runs(self, r: PackedRuns):
         desc = np.ascontiguousarray(r.desc)
@@ -241,7 +261,10 @@ class BatchEngine:
         """upload -> merge -> download.  The comment pool has a default capacity; a log whose comment lists do not fit
         reports status 4 without consuming pool space and the engine reports the batch's exact demand, so one re-merge
         with a pool of that size always succeeds (documents with many overlapping comments are valid input)."""
-        self.upload(batch); self.merge(); out = self.download()
+        self.upload(batch)
+        if getattr(batch, "changes", None) is not None:
+            self.upload_changes(batch.changes)
+        self.merge(); out = self.download()
         if len(out.results) and (out.results["status"] == 4).any() and self.comment_pool_needed > self.comment_pool_used:
             self.set_comment_pool(self.comment_pool_needed + 16)
             self.merge(); out = self.download()
@@ -292,3 +315,55 @@ class PipelinedEngine:
     def close(self):
         for e in self.engines:
             e.close()
+
+
+def pack_logs_native(logs_json, threads: int = 0) -> PackedBatch:
+    """Native (C++, multithreaded) wire-format ingest: ``logs_json[i]`` = JSON text (str or bytes) of the Change objects
+    replica i applied, in arrival order -> PackedBatch with its change table (csrc/ingest.cpp, pt_ingest_*).  Packs exactly
+    like ``packing.pack_logs(..., with_changes=True)``."""
+    import json
+    L = load_library()
+    blobs = [s.encode("utf-8", "surrogatepass") if isinstance(s, str) else bytes(s) for s in logs_json]
+    n = len(blobs)
+    ptrs = (ctypes.c_char_p * max(1, n))(*blobs) if n else (ctypes.c_char_p * 1)()
+    lens = (ctypes.c_uint64 * max(1, n))(*[len(b) for b in blobs]) if n else (ctypes.c_uint64 * 1)()
+    h = ctypes.c_void_p()
+    _check(L.pt_ingest_create(ctypes.byref(h)), "pt_ingest_create")
+    try:
+        rc = L.pt_ingest_parse(h, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(lens, ctypes.c_void_p), n, threads)
+        if rc != 0:
+            raise ValueError(L.pt_ingest_error(h).decode("utf-8", "replace"))
+        ops, tab = _PackedOps(), _ChangeTable()
+        _check(L.pt_ingest_packed(h, ctypes.byref(ops), ctypes.byref(tab)), "pt_ingest_packed")
+
+        def arr(ptr, count, dt):
+            if not count or not ptr:
+                return np.zeros(0, dt)
+            buf = (ctypes.c_char * (count * np.dtype(dt).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dt, count=count).copy()
+
+        def pool(kind):
+            data, off, cnt, first = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_void_p()
+            _check(L.pt_ingest_pool(h, kind, ctypes.byref(data), ctypes.byref(off), ctypes.byref(cnt), ctypes.byref(first)), "pt_ingest_pool")
+            o = arr(off.value, cnt.value + 1, np.uint64)
+            raw = bytes(arr(data.value, int(o[-1]), np.uint8)) if cnt.value else b""
+            items = [raw[int(o[k]): int(o[k + 1])] for k in range(cnt.value)]
+            f = arr(first.value, n + 1, np.uint64) if first.value else None
+            return items, f
+
+        u16 = lambda b: b.decode("utf-16-le", "surrogatepass")
+        values = [u16(b) for b in pool(0)[0]]
+        link_attrs = [json.loads(b.decode("utf-8", "surrogatepass")) for b in pool(1)[0]]
+        comment_attrs = [json.loads(b.decode("utf-8", "surrogatepass")) for b in pool(3)[0]]
+        actors, afirst = pool(4)
+        counters, cfirst = pool(5)
+        log_actors = [[u16(x) for x in actors[int(afirst[i]): int(afirst[i + 1])]] for i in range(n)]
+        log_counters = []
+        for i in range(n):
+            c = counters[int(cfirst[i]): int(cfirst[i + 1])]
+            log_counters.append(np.array([int.from_bytes(x, "little") for x in c], dtype=np.uint64) if c else None)
+        table = ChangeTable(arr(tab.logs, tab.n_logs, CDESC_DT), arr(tab.changes, tab.n_changes_total, CHANGE_DT), arr(tab.deps, tab.n_deps_total, DEP_DT))
+        return PackedBatch(arr(ops.logs, ops.n_logs, DESC_DT), arr(ops.insdel, ops.n_insdel_total, INSDEL_DT), arr(ops.marks, ops.n_mark_total, MARK_DT),
+                           values, link_attrs, comment_attrs, [], log_actors=log_actors, log_counters=log_counters, changes=table)
+    finally:
+        L.pt_ingest_destroy(h)

@@ -29,6 +29,10 @@ DESC_DT = np.dtype([("insdel_off", "<u8"), ("mark_off", "<u8"), ("n_insdel", "<u
 RESULT_DT = np.dtype([("status", "<u4"), ("n_elems", "<u4"), ("n_visible", "<u4"), ("n_spans", "<u4"),
                       ("digest", "<u8", (2,))])
 SPAN_DT = np.dtype([("start", "<u4"), ("flags", "<u4"), ("link_attr", "<u4"), ("comment_off", "<u4")])
+CHANGE_DT = np.dtype([("seq", "<u4"), ("actor", "<u2"), ("n_deps", "<u2"), ("dep_off", "<u4"), ("n_ops", "<u4")])
+DEP_DT = np.dtype([("seq", "<u4"), ("actor", "<u2"), ("reserved", "<u2")])
+CDESC_DT = np.dtype([("change_off", "<u8"), ("dep_off", "<u8"), ("n_changes", "<u4"), ("n_deps", "<u4")])
+assert CHANGE_DT.itemsize == 16 and DEP_DT.itemsize == 8 and CDESC_DT.itemsize == 24
 assert INSDEL_DT.itemsize == 16 and MARK_DT.itemsize == 32 and DESC_DT.itemsize == 32
 assert RESULT_DT.itemsize == 32 and SPAN_DT.itemsize == 16
 
@@ -40,7 +44,7 @@ BOUND_TYPES = ["before", "after", "startOfText", "endOfText"]
 SPAN_STRONG, SPAN_EM, SPAN_LINK, SPAN_COMMENT = 1, 2, 4, 8
 
 LOG_STATUS = {0: "ok", 1: "List element not found", 2: "bad opId", 3: "bad record kind", 4: "capacity overflow",
-              5: "reference element does not precede insert"}
+              5: "reference element does not precede insert", 6: "Expected sequence number", 7: "Missing dependency"}
 
 _OPID_RE = re.compile(r"^([0-9]+)@(.*)$", re.S)  # reference src/micromerge.ts:815
 
@@ -74,6 +78,7 @@ class PackedBatch:
     meta: dict = field(default_factory=dict)
     log_actors: list[list[str]] = field(default_factory=list)   # per log: actor rank -> actorId
     log_counters: list = field(default_factory=list)            # per log: None, or dense counter rank -> original counter
+    changes: Any = None                                         # optional ChangeTable (admission pre-pass)
 
     @property
     def n_logs(self) -> int:
@@ -125,6 +130,15 @@ class PackedBatch:
         return b
 
 
+@dataclass
+class ChangeTable:
+    """Per-change admission records (include/peritext_b200.h pt_change_table): what Micromerge.applyChange checks before
+    applying a change (reference src/micromerge.ts:499-511)."""
+    desc: np.ndarray      # CDESC_DT [n_logs]
+    changes: np.ndarray   # CHANGE_DT
+    deps: np.ndarray      # DEP_DT
+
+
 class _LogBuilder:
     """Collects one log's ops (arrival order) before ranks are known."""
 
@@ -133,6 +147,7 @@ class _LogBuilder:
         self.marks: list[tuple] = []    # (ctr, actor, add, mtype, sb, (sctr, sactor), eb, (ectr, eactor), attrs, arrival)
         self.actors: set[str] = set()
         self.max_ctr = 0
+        self.changes: list[tuple] = []  # (actor, seq, [(dep actor, dep seq)...], n list ops)
 
 
 def _root_text_list(changes: Iterable[dict]) -> str | None:
@@ -157,11 +172,13 @@ def _root_text_list(changes: Iterable[dict]) -> str | None:
     return children.get("text")
 
 
-def pack_logs(logs: Sequence[Sequence[dict]], *, list_ids: Sequence[str | None] | None = None) -> PackedBatch:
+def pack_logs(logs: Sequence[Sequence[dict]], *, list_ids: Sequence[str | None] | None = None, with_changes: bool = False) -> PackedBatch:
     """Pack ``logs[i]`` = the Change objects one replica applied, in arrival order.
 
     Ops that do not target the log's text list (ROOT-map ops, other lists) are host-side bookkeeping and are not
-    packed.  ``list_ids[i]`` overrides the list object id (default: what ``["text"]`` resolves to)."""
+    packed.  ``list_ids[i]`` overrides the list object id (default: what ``["text"]`` resolves to).  ``with_changes``
+    also builds the per-change admission table (then the change / deps actors take part in the log's actor ranking).
+    The native, multithreaded equivalent over JSON text is ``pack_logs_native`` (csrc/ingest.cpp)."""
     builders: list[_LogBuilder] = []
     values: list[str] = []
     value_index: dict[str, int] = {}
@@ -187,9 +204,17 @@ def pack_logs(logs: Sequence[Sequence[dict]], *, list_ids: Sequence[str | None] 
         b = _LogBuilder()
         lid = list_ids[li] if list_ids is not None and list_ids[li] is not None else _root_text_list(changes)
         for ch in changes:
+            if with_changes:
+                b.actors.add(ch["actor"])
+                deps = list((ch.get("deps") or {}).items())
+                for a, _ in deps:
+                    b.actors.add(a)
+                b.changes.append([ch["actor"], int(ch["seq"]), [(a, int(v)) for a, v in deps], 0])
             for op in ch["ops"]:
                 if lid is None or op.get("obj") != lid:
                     continue
+                if with_changes:
+                    b.changes[-1][3] += 1
                 ctr, actor = parse_op_id(op["opId"])
                 b.actors.add(actor)
                 b.max_ctr = max(b.max_ctr, ctr)
@@ -294,8 +319,24 @@ def pack_logs(logs: Sequence[Sequence[dict]], *, list_ids: Sequence[str | None] 
                              dc(sb[1]), dc(eb[1]), rank[sb[2]] if sb[2] is not None else 0,
                              rank[eb[2]] if eb[2] is not None else 0, attr, arrival, 0)
         io += len(b.insdel); mo += len(b.marks)
+    table = None
+    if with_changes:
+        cdesc = np.zeros(len(builders), CDESC_DT)
+        crecs = np.zeros(sum(len(b.changes) for b in builders), CHANGE_DT)
+        cdeps = np.zeros(sum(len(c[2]) for b in builders for c in b.changes), DEP_DT)
+        co = do = 0
+        for li, b in enumerate(builders):
+            rank = {a: i for i, a in enumerate(sorted(b.actors, key=js_key))}
+            nd = 0
+            cdesc[li]["change_off"] = co; cdesc[li]["dep_off"] = do; cdesc[li]["n_changes"] = len(b.changes)
+            for (actor, seq, deps, n_ops) in b.changes:
+                crecs[co] = (seq, rank[actor], len(deps), nd, n_ops); co += 1
+                for a, v in deps:
+                    cdeps[do] = (v, rank[a], 0); do += 1; nd += 1
+            cdesc[li]["n_deps"] = nd
+        table = ChangeTable(cdesc, crecs, cdeps)
     return PackedBatch(desc, insdel, marks, values, link_attrs, [comment_objs[c] for c in comment_sorted], other_attrs,
-                       log_actors=[sorted(b.actors, key=js_key) for b in builders], log_counters=counters)
+                       log_actors=[sorted(b.actors, key=js_key) for b in builders], log_counters=counters, changes=table)
 
 
 # ------------------------------------------------------------------------------------------------------------------

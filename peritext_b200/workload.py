@@ -89,3 +89,48 @@ def generate(config: str, *, n_docs: int | None = None, ops_per_doc: int | None 
                                   ops_per_doc=cfg["ops_per_doc"], unique_ops=int(b.unique_ops), seed=seed, doc_first=doc_first))
     L.ptw_free(out)
     return batch
+
+
+def to_change_json(batch: PackedBatch, i: int) -> str:
+    """Log i of a generated batch as the reference's wire format (JSON text of Change objects, one op per change) — the
+    input of the native ingest path (`engine.pack_logs_native`); used to measure ingest throughput and to test the ingest on
+    the benchmark shapes.  Actor rank r becomes "doc{r+1}", the list is "1@doc1" (the generator's first insert has ctr 2)."""
+    import json
+    ins, mk = batch.log_slice(i)
+    name = lambda r: "doc%d" % (int(r) + 1)
+    oid = lambda c, a: "%d@%s" % (int(c), name(a))
+    lid = "1@doc1"
+    seqs: dict = {}
+    out = [{"actor": "doc1", "seq": 1, "deps": {}, "startOp": 1, "ops": [{"opId": lid, "action": "makeList", "obj": "_root", "key": "text"}]}]
+    seqs["doc1"] = 1
+    btypes = ["before", "after", "startOfText", "endOfText"]
+    mtypes = ["strong", "em", "comment", "link"]
+
+    def emit(actor, ctr, op):
+        a = name(actor)
+        seqs[a] = seqs.get(a, 0) + 1
+        out.append({"actor": a, "seq": seqs[a], "deps": {}, "startOp": int(ctr), "ops": [op]})
+    k = 0
+    for j in range(len(ins) + 1):
+        while k < len(mk) and int(mk[k]["arrival"]) == j:
+            r = mk[k]; k += 1
+            kind, mt = int(r["kind"]) & 1, (int(r["kind"]) >> 1) & 3
+            sb, eb = int(r["bounds"]) & 3, (int(r["bounds"]) >> 2) & 3
+            op = {"opId": oid(r["ctr"], r["actor"]), "action": "removeMark" if kind else "addMark", "obj": lid, "markType": mtypes[mt],
+                  "start": {"type": btypes[sb], **({"elemId": oid(r["start_ctr"], r["start_actor"])} if sb <= 1 else {})},
+                  "end": {"type": btypes[eb], **({"elemId": oid(r["end_ctr"], r["end_actor"])} if eb <= 1 else {})}}
+            if mt == 3 and not kind:
+                op["attrs"] = batch.link_attrs[int(r["attr"])]
+            elif mt == 2:
+                op["attrs"] = batch.comment_ids[int(r["attr"])]
+            emit(r["actor"], r["ctr"], op)
+        if j == len(ins):
+            break
+        r = ins[j]
+        if int(r["payload"]) >> 30 == 0:
+            op = {"opId": oid(r["ctr"], r["actor"]), "action": "set", "obj": lid, "insert": True, "value": chr(int(r["payload"]) & 0x1FFFFFFF),
+                  "elemId": oid(r["ref_ctr"], r["ref_actor"]) if int(r["ref_ctr"]) else "_head"}
+        else:
+            op = {"opId": oid(r["ctr"], r["actor"]), "action": "del", "obj": lid, "elemId": oid(r["ref_ctr"], r["ref_actor"])}
+        emit(r["actor"], r["ctr"], op)
+    return json.dumps(out, separators=(",", ":"))
