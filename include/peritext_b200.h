@@ -230,9 +230,38 @@ typedef struct pt_spans_view {
 typedef struct pt_limits {
     uint64_t comment_pool_entries; /* 0: 64 x number of mark ops in the batch (+slack)            */
     uint32_t flags;                /* PT_FLAG_*                                                     */
-    uint32_t reserved[5];
+    uint32_t patch_pool_items;     /* 0: 4 x number of op records in the batch (+slack)            */
+    uint32_t reserved[4];
 } pt_limits;
 #define PT_FLAG_EMIT_SEQUENCE 1u   /* also emit the element sequence (needed by op generation / cursors on the host) */
+#define PT_FLAG_EMIT_PATCHES 2u    /* also derive the Patch stream of every op on the device (implies EMIT_SEQUENCE) */
+
+/* ------------------------------------------------------------------------------------------------
+ * Patch stream (PT_FLAG_EMIT_PATCHES): what Micromerge.applyChange returns for every op of a log, given the
+ * log's arrival order (src/micromerge.ts:659-671, 689-703; src/peritext.ts:175-220, 251-281).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_patch_rec {   /* one per ins/del record, at the record's offset. 16 B */
+    uint32_t index;     /* bits30:0: Patch.index (visible elements left of the op's element at apply time);
+                           bit31: the op emits a patch (inserts always; a delete only if it is the element's first) */
+    uint32_t flags;     /* insert: the `marks` of the patch = marks inherited from the left neighbour at apply time
+                           (getActiveMarksAtIndex, src/peritext.ts:328): PT_SPAN_* bits, bits31:8 number of comment ids  */
+    uint32_t link_attr; /* url id if PT_SPAN_LINK                                                                 */
+    uint32_t reserved;
+} pt_patch_rec;
+typedef struct pt_patch_item {  /* pool entry, any order. 16 B */
+    uint32_t log;       /* log index                                                                             */
+    uint32_t tag;       /* bit31 set: mark patch of mark record (tag & 0x7FFFFFFF): a = startIndex, b = endIndex;
+                           bit31 clear: comment id `a` in the `marks` of the insert patch of ins/del record `tag`       */
+    uint32_t a, b;
+} pt_patch_item;
+typedef struct pt_patch_view {
+    const pt_patch_rec* recs;      /* [n_insdel_total]                                                            */
+    const pt_patch_item* items;    /* [n_items]                                                                   */
+    uint64_t n_items;
+    uint64_t n_items_needed;       /* > the pool's capacity: call pt_batch_set_patch_pool(needed) and merge again */
+    const uint32_t* status;        /* [n_logs] 0: computed; 1: not computed (log too large for the device patch kernel or
+                                      merge failed) — derive on the host                                          */
+} pt_patch_view;
 
 typedef enum pt_status {
     PT_OK = 0,
@@ -287,6 +316,11 @@ int pt_batch_download_begin(pt_batch*);
 
 /* Copy results device -> host (pinned) and return a view. Synchronises the stream. */
 int pt_batch_download(pt_batch*, pt_spans_view* out);
+
+/* PT_FLAG_EMIT_PATCHES: copy the Patch stream of the last merge device -> host and return a view (engine-owned pinned
+ * memory, valid until the next upload / destroy). Synchronises. */
+int pt_batch_download_patches(pt_batch*, pt_patch_view* out);
+int pt_batch_set_patch_pool(pt_batch*, uint64_t items);
 
 /* Copy only the per-log result headers (status, counts, digest). Synchronises the stream. */
 int pt_batch_download_results(pt_batch*, pt_log_result* out, uint32_t n_logs);

@@ -12,6 +12,7 @@
 
 #include "merge_kernel.cuh"
 #include "warp_kernel.cuh"
+#include "patch_kernel.cuh"
 
 namespace {
 
@@ -313,6 +314,10 @@ struct pt_batch {
     DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_slab, d_retry, d_seq;
     DevBuf d_bsum, d_ctoff, d_csoff, d_ctext, d_cspans;   // download path: packed outputs + their offsets ([n_logs + 1])
     DevBuf d_cdesc, d_changes, d_deps, d_admit;           // admission pre-pass (optional change table)
+    DevBuf d_patch_recs, d_patch_items, d_patch_status;   // PT_FLAG_EMIT_PATCHES
+    HostBuf h_patch_recs, h_patch_items, h_patch_status, h_patch_misc;
+    uint64_t patch_cap = 0;
+    uint32_t patch_smem = 0;
     bool have_changes = false;
     uint32_t adm_maxR = 1;
     const pt_insdel_rec* dp_insdel = nullptr;
@@ -444,6 +449,22 @@ int alloc_and_upload_plan(pt_batch* b) {
     if ((rc = b->d_spans.reserve(std::max<uint64_t>(1, b->n_span) * sizeof(pt_span)))) return rc;
     if ((rc = b->d_pool.reserve(std::max<uint64_t>(1, b->pool_cap) * 4))) return rc;
     if ((rc = b->d_retry.reserve(std::max<size_t>(1, n) * 4 * kNumBins + 16))) return rc;
+    if (b->limits.flags & PT_FLAG_EMIT_PATCHES) {
+        b->patch_cap = b->limits.patch_pool_items ? b->limits.patch_pool_items : 4ull * (b->n_insdel + b->n_mark) + 1024;
+        if ((rc = b->d_patch_recs.reserve(std::max<uint64_t>(1, b->n_insdel) * sizeof(pt_patch_rec)))) return rc;
+        if ((rc = b->d_patch_items.reserve(std::max<uint64_t>(1, b->patch_cap) * sizeof(pt_patch_item)))) return rc;
+        if ((rc = b->d_patch_status.reserve(std::max<size_t>(1, n) * 4))) return rc;
+        // one warp per CTA; shared memory = the largest footprint among the logs, capped (larger logs are left to the host)
+        uint64_t need_max = 4096;
+        for (uint32_t i = 0; i < b->n_logs; i++) {
+            const pt_log_desc& L = b->h_desc[i];
+            const uint64_t KS = (uint64_t)L.max_ctr * (L.n_actors ? L.n_actors : 1);
+            const uint64_t need = ((KS * 2 + 15) & ~15ull) + 3 * (((uint64_t)L.n_insdel * 2 + 15) & ~15ull) / 1 + (((uint64_t)L.n_insdel * 4 + 15) & ~15ull) +
+                                  6 * (((uint64_t)L.n_mark * 4 + 15) & ~15ull) + (((uint64_t)L.n_mark * 2 + 15) & ~15ull) + 256;
+            if (need <= 200 * 1024) need_max = std::max(need_max, need);
+        }
+        b->patch_smem = (uint32_t)((need_max + 1023) & ~1023ull);
+    }
     size_t slab_total = 0, slab_max = 0;
     for (int k = 0; k < kNumBins; k++) slab_max = std::max(slab_max, b->bin_slab[k]);
     slab_total = (size_t)b->num_sms * kBins[kNumBins - 1].ctas_per_sm * slab_max;   // only the last bin can spill
@@ -563,6 +584,7 @@ int pt_batch_create(int device, const pt_limits* limits, void* cuda_stream, pt_b
     pt_batch* b = new pt_batch();
     b->device = device; b->stream = (cudaStream_t)cuda_stream; b->num_sms = prop.multiProcessorCount;
     if (limits) b->limits = *limits;
+    if (b->limits.flags & PT_FLAG_EMIT_PATCHES) b->limits.flags |= PT_FLAG_EMIT_SEQUENCE;
     if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) { delete b; g_last_error = "cudaEventCreate failed"; return PT_ERR_CUDA; }
     *out = b;
     return PT_OK;
@@ -746,6 +768,20 @@ static int enqueue_merge(pt_batch* b) {
         if (k > 0 && lower && (rc = launch_bin(b, k, P, true))) return rc;
         lower = lower || b->bin_first[k + 1] > b->bin_first[k];
     }
+    if ((b->limits.flags & PT_FLAG_EMIT_PATCHES) && b->n_logs) {
+        ptk::PatchParams Q{};
+        Q.desc = P.desc; Q.insdel = P.insdel; Q.marks = P.marks; Q.results = P.results; Q.text_off = P.text_off; Q.seq = P.seq;
+        Q.n_logs = b->n_logs; Q.smem_bytes = b->patch_smem;
+        Q.recs = (pt_patch_rec*)b->d_patch_recs.p; Q.items = (pt_patch_item*)b->d_patch_items.p;
+        Q.item_cursor = (unsigned long long*)((char*)b->d_counters.p + 80); Q.item_cap = b->patch_cap;
+        Q.status = (uint32_t*)b->d_patch_status.p;
+        PT_CUDA(cudaFuncSetAttribute(ptk::patch_logs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->patch_smem));
+        const uint32_t per_sm = std::max<uint32_t>(1, std::min<uint32_t>(32, (227u * 1024u) / (b->patch_smem + 1024u)));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(b->n_logs, (uint64_t)b->num_sms * per_sm);
+        ptk::patch_logs_kernel<<<grid, 32, b->patch_smem, b->stream>>>(Q);
+        PT_CUDA(cudaGetLastError());
+        b->launches++;
+    }
     return PT_OK;
 }
 
@@ -892,6 +928,41 @@ int pt_batch_download(pt_batch* b, pt_spans_view* out) {
     return PT_OK;
 }
 
+int pt_batch_download_patches(pt_batch* b, pt_patch_view* out) {
+    if (!b || !out) return PT_ERR_INVALID;
+    if (!b->merged) { g_last_error = "download before merge"; return PT_ERR_STATE; }
+    if (!(b->limits.flags & PT_FLAG_EMIT_PATCHES)) { g_last_error = "the handle was created without PT_FLAG_EMIT_PATCHES"; return PT_ERR_STATE; }
+    int rc;
+    if ((rc = b->h_patch_misc.reserve(16))) return rc;
+    if ((rc = b->h_patch_recs.reserve(std::max<uint64_t>(1, b->n_insdel) * sizeof(pt_patch_rec)))) return rc;
+    if ((rc = b->h_patch_status.reserve(std::max<size_t>(1, b->n_logs) * 4))) return rc;
+    PT_CUDA(cudaMemcpyAsync(b->h_patch_misc.p, (char*)b->d_counters.p + 80, 8, cudaMemcpyDeviceToHost, b->stream));
+    if (b->n_insdel) PT_CUDA(cudaMemcpyAsync(b->h_patch_recs.p, b->d_patch_recs.p, b->n_insdel * sizeof(pt_patch_rec), cudaMemcpyDeviceToHost, b->stream));
+    if (b->n_logs) PT_CUDA(cudaMemcpyAsync(b->h_patch_status.p, b->d_patch_status.p, (size_t)b->n_logs * 4, cudaMemcpyDeviceToHost, b->stream));
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    const uint64_t demand = *(unsigned long long*)b->h_patch_misc.p, used = std::min<uint64_t>(demand, b->patch_cap);
+    if ((rc = b->h_patch_items.reserve(std::max<uint64_t>(1, used) * sizeof(pt_patch_item)))) return rc;
+    if (used) { PT_CUDA(cudaMemcpyAsync(b->h_patch_items.p, b->d_patch_items.p, used * sizeof(pt_patch_item), cudaMemcpyDeviceToHost, b->stream)); PT_CUDA(cudaStreamSynchronize(b->stream)); }
+    out->recs = (const pt_patch_rec*)b->h_patch_recs.p; out->items = (const pt_patch_item*)b->h_patch_items.p;
+    out->n_items = used; out->n_items_needed = demand; out->status = (const uint32_t*)b->h_patch_status.p;
+    return PT_OK;
+}
+
+int pt_batch_set_patch_pool(pt_batch* b, uint64_t items) {
+    if (!b || items > 0xFFFFFFFFull) return PT_ERR_INVALID;
+    PT_CUDA(cudaSetDevice(b->device));
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    b->limits.patch_pool_items = (uint32_t)items;
+    if (b->have_batch && items && (b->limits.flags & PT_FLAG_EMIT_PATCHES)) {
+        b->patch_cap = items;
+        int rc;
+        if ((rc = b->d_patch_items.reserve(b->patch_cap * sizeof(pt_patch_item)))) return rc;
+        if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
+        b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0;
+    }
+    return PT_OK;
+}
+
 int pt_batch_device_results(pt_batch* b, void** dev_ptr, uint32_t* n_logs) {
     if (!b || !dev_ptr) return PT_ERR_INVALID;
     if (!b->have_batch) return PT_ERR_STATE;
@@ -938,7 +1009,8 @@ void pt_batch_destroy(pt_batch* b) {
     for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
                       &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_slab, &b->d_retry, &b->d_seq,
                       &b->d_runs, &b->d_tokens, &b->d_run_off, &b->d_tok_off, &b->d_bsum, &b->d_ctoff, &b->d_csoff, &b->d_ctext, &b->d_cspans,
-                      &b->d_cdesc, &b->d_changes, &b->d_deps, &b->d_admit}) d->release();
+                      &b->d_cdesc, &b->d_changes, &b->d_deps, &b->d_admit, &b->d_patch_recs, &b->d_patch_items, &b->d_patch_status}) d->release();
+    for (HostBuf* h : {&b->h_patch_recs, &b->h_patch_items, &b->h_patch_status, &b->h_patch_misc}) h->release();
     for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc, &b->h_seq, &b->h_ctoff, &b->h_csoff}) h->release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);

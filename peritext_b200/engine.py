@@ -20,7 +20,7 @@ _lib = None
 EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_upload_runs", "pt_compress_runs", "pt_batch_adopt_device", "pt_batch_upload_changes",
            "pt_ingest_create", "pt_ingest_parse", "pt_ingest_packed", "pt_ingest_pool", "pt_ingest_error", "pt_ingest_destroy", "pt_batch_merge", "pt_batch_sync",
            "pt_batch_download", "pt_batch_download_begin", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count", "pt_batch_stats",
-           "pt_batch_last_merge_ms", "pt_batch_set_comment_pool", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
+           "pt_batch_last_merge_ms", "pt_batch_set_comment_pool", "pt_batch_download_patches", "pt_batch_set_patch_pool", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
 
 
 class EngineError(RuntimeError):
@@ -101,10 +101,19 @@ class _SpansView(ctypes.Structure):
 
 
 class _Limits(ctypes.Structure):
-    _fields_ = [("comment_pool_entries", ctypes.c_uint64), ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 5)]
+    _fields_ = [("comment_pool_entries", ctypes.c_uint64), ("flags", ctypes.c_uint32), ("patch_pool_items", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32 * 4)]
 
 
+class _PatchView(ctypes.Structure):
+    _fields_ = [("recs", ctypes.c_void_p), ("items", ctypes.c_void_p), ("n_items", ctypes.c_uint64), ("n_items_needed", ctypes.c_uint64),
+                ("status", ctypes.c_void_p)]
+
+
+PATCH_REC_DT = np.dtype([("index", "<u4"), ("flags", "<u4"), ("link_attr", "<u4"), ("reserved", "<u4")])
+PATCH_ITEM_DT = np.dtype([("log", "<u4"), ("tag", "<u4"), ("a", "<u4"), ("b", "<u4")])
 FLAG_EMIT_SEQUENCE = 1
+FLAG_EMIT_PATCHES = 2
 
 
 def load_library() -> ctypes.CDLL:
@@ -138,6 +147,8 @@ def load_library() -> ctypes.CDLL:
     L.pt_batch_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 4)]
     L.pt_batch_last_merge_ms.argtypes = [vp]; L.pt_batch_last_merge_ms.restype = ctypes.c_float
     L.pt_batch_set_comment_pool.argtypes = [vp, u64]
+    L.pt_batch_download_patches.argtypes = [vp, vp]
+    L.pt_batch_set_patch_pool.argtypes = [vp, u64]
     L.pt_batch_destroy.argtypes = [vp]; L.pt_batch_destroy.restype = None
     L.pt_strerror.argtypes = [ctypes.c_int]; L.pt_strerror.restype = ctypes.c_char_p
     L.pt_last_error.restype = ctypes.c_char_p
@@ -155,11 +166,14 @@ def _check(rc: int, what: str):
 class BatchEngine:
     """One handle per (GPU, batch).  ``upload`` -> ``merge`` -> ``download``."""
 
-    def __init__(self, device: int = 0, stream: int | None = None, comment_pool_entries: int = 0, emit_sequence: bool = False):
+    def __init__(self, device: int = 0, stream: int | None = None, comment_pool_entries: int = 0, emit_sequence: bool = False,
+                 emit_patches: bool = False):
         L = load_library()
         self._L = L
         self._h = ctypes.c_void_p()
-        lim = _Limits(comment_pool_entries, FLAG_EMIT_SEQUENCE if emit_sequence else 0, (ctypes.c_uint32 * 5)())
+        self.emit_patches = emit_patches
+        flags = (FLAG_EMIT_SEQUENCE if (emit_sequence or emit_patches) else 0) | (FLAG_EMIT_PATCHES if emit_patches else 0)
+        lim = _Limits(comment_pool_entries, flags, 0, (ctypes.c_uint32 * 4)())
         _check(L.pt_batch_create(device, ctypes.byref(lim), ctypes.c_void_p(stream or 0), ctypes.byref(self._h)), "pt_batch_create")
         self._keep = None
         self.n_logs = 0
@@ -174,6 +188,7 @@ class BatchEngine:
         ops = self._ops_struct(desc, insdel.ctypes.data, len(insdel), marks.ctypes.data, len(marks))
         _check(self._L.pt_batch_upload(self._h, ctypes.byref(ops)), "pt_batch_upload")
         self.n_logs = len(desc)
+        self._n_insdel = len(insdel)
 
     def upload_changes(self, table: ChangeTable):
         """Attach the batch's change table: the next merge runs the admission pre-pass (seq / deps checks of
@@ -253,6 +268,29 @@ class BatchEngine:
         return MergedBatch(results, text_off, span_off, arr(v.text, n_text, np.uint32), arr(v.spans, n_span, SPAN_DT),
                            arr(v.comment_pool, int(v.comment_pool_used), np.uint32),
                            arr(v.seq, n_seq, np.uint32) if v.seq else None, seq_off)
+
+    def download_patches(self):
+        """PT_FLAG_EMIT_PATCHES: (patch records per ins/del record, pool items, per-log status, items needed) of the last merge."""
+        v = _PatchView()
+        _check(self._L.pt_batch_download_patches(self._h, ctypes.byref(v)), "pt_batch_download_patches")
+
+        def arr(ptr, count, dt):
+            if not count or not ptr:
+                return np.zeros(0, dt)
+            buf = (ctypes.c_char * (count * np.dtype(dt).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dt, count=count).copy()
+        return arr(v.recs, self._n_insdel, PATCH_REC_DT), arr(v.items, int(v.n_items), PATCH_ITEM_DT), arr(v.status, self.n_logs, np.uint32), int(v.n_items_needed)
+
+    def run_with_patches(self, batch: PackedBatch):
+        """upload -> merge (+ device Patch stream) -> download; returns (MergedBatch, DevicePatches)."""
+        out = self.run(batch)
+        recs, items, status, needed = self.download_patches()
+        if needed > len(items):
+            _check(self._L.pt_batch_set_patch_pool(self._h, needed + 16), "pt_batch_set_patch_pool")
+            self.merge(); out = self.download()
+            recs, items, status, needed = self.download_patches()
+        from .packing import DevicePatches
+        return out, DevicePatches(recs, items, status)
 
     def set_comment_pool(self, entries: int):
         _check(self._L.pt_batch_set_comment_pool(self._h, int(entries)), "pt_batch_set_comment_pool")

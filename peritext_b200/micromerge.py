@@ -8,16 +8,25 @@
   applied to the host mirror incrementally (their opIds are larger than everything known, so they land right after their
   reference element); remote changes invalidate the mirror and the next access re-materialises on the GPU.
 
-* The Patch stream (`applyChange` / `change` return values) is derived on the host with the
-  order-independent closed forms of `peritext_b200/patches.py` from the element positions the engine materialised and the
-  arrival times this facade recorded — one GPU materialisation per `applyChange`.  (A batched device version is round-2
-  work; this path serves the interactive single-document use of `bridge.ts`.)
+* The Patch stream (`applyChange` / `applyChanges` return values) comes from the device: the engine
+  is created with `PT_FLAG_EMIT_PATCHES` and the patch kernel (csrc/patch_kernel.cuh) derives the patches of every op of
+  the log in the same pass that materialises the document.  `applyChanges(changes)` admits a whole list of changes (causal
+  retry, as the reference's test/merge.ts:4-23) and derives all their patches in ONE device pass; `applyChange` is the
+  batch of one.  Logs too large for the device patch kernel, and the ops `change()` generates locally (applied to the host
+  mirror without touching the GPU), use the same closed forms on the host (`peritext_b200/patches.py`).
+
+Deviations from the reference class, all at the admission boundary (documented, tested in tests/test_facade.py):
+  * an insert whose opId is SMALLER than its reference element's (a hand-made change that chose a startOp below an element
+    it depends on) is refused by `applyChange` with RangeError — the reference would merge it; the engine's closed form
+    needs Lamport counters (the reference's own `change()` always produces them, src/micromerge.ts:487, 511);
+  * `applyChange` validates the objects of ALL ops of a change before it bumps the clock (the reference bumps first and
+    applies ops up to the failing one).
 """
 from __future__ import annotations
 
 import copy
 
-from .packing import RangeError, _root_text_list, decode_spans, js_key, pack_logs, parse_op_id, token_str
+from .packing import RangeError, _root_text_list, decode_spans, js_key, pack_logs, parse_op_id, patch_stream, token_str
 from .patches import ArrivalHistory, derive_patch
 
 _default_engine = None
@@ -28,7 +37,7 @@ def default_engine():
     global _default_engine
     if _default_engine is None:
         from .engine import BatchEngine
-        _default_engine = BatchEngine(0, emit_sequence=True)
+        _default_engine = BatchEngine(0, emit_sequence=True, emit_patches=True)
     return _default_engine
 
 
@@ -65,9 +74,31 @@ class Micromerge:
         self._hist = ArrivalHistory()         # arrival times of the current text list's ops (for the Patch closed forms)
         self._hist_list = None
         self._root_keys: dict[str, str] = {}  # ROOT map: key -> opId that last won LWW (src/micromerge.ts:584-586)
+        self._root_vals: dict[str, object] = {}   # ROOT map: primitive values / child placeholders of the keys other than "text"
 
     # -- reference src/micromerge.ts:499-514 --------------------------------------------------------------------------
     def applyChange(self, change: dict) -> list:
+        self._admit(change)
+        return self._patches_for(change["ops"], local=False)
+
+    def applyChanges(self, changes: list) -> list:
+        """Admit a list of changes with causal retry (a change whose dependencies are not there yet goes back to the end of
+        the queue — the reference's test helper test/merge.ts:4-23) and return the concatenated Patch lists: ONE device pass
+        materialises the document and derives every patch."""
+        queue, order, iterations = list(changes), [], 0
+        while queue:
+            ch = queue.pop(0)
+            try:
+                self._admit(ch)
+                order.append(ch)
+            except RangeError:
+                queue.append(ch)
+            iterations += 1
+            if iterations > 10000:
+                raise RuntimeError("applyChanges did not converge")
+        return self._patches_for([op for ch in order for op in ch["ops"]], local=False)
+
+    def _admit(self, change: dict):
         lastSeq = self.clock.get(change["actor"], 0)
         if change["seq"] != lastSeq + 1:
             raise RangeError(f"Expected sequence number {lastSeq + 1}, got {change['seq']}")
@@ -82,13 +113,14 @@ class Micromerge:
             parse_op_id(op["opId"])
             if op["action"] in ("makeList", "makeMap"):
                 created[op["opId"]] = "list" if op["action"] == "makeList" else "map"
+            if op["action"] == "set" and op.get("insert") and op.get("elemId") not in (None, "_head") and compareOpIds(op["opId"], op["elemId"]) <= 0:
+                raise RangeError(f"insert {op['opId']} does not follow its reference element {op['elemId']} in Lamport order")
         self._objects.update(created)
         self.clock[change["actor"]] = change["seq"]
         self._maxOp = max(self._maxOp, change["startOp"] + len(change["ops"]) - 1)
         self._applied.append(copy.deepcopy(change))                  # Change objects passed in are not mutated
         self._cache = None
         self._mirror = None
-        return self._patches_for(change["ops"], local=False)
 
     # -- Patch[] of a list of ops that were just appended to the log (closed forms, peritext_b200/patches.py) ------------
     def _root_op(self, op) -> list:
@@ -99,6 +131,13 @@ class Micromerge:
         cur = self._root_keys.get(key)
         if cur is None or compareOpIds(cur, op["opId"]) == -1:
             self._root_keys[key] = op["opId"]
+            if key != "text":                                   # :586-603: the winner's value (child objects other than the text list are
+                if op["action"] == "set":                       # not materialised by this engine: empty placeholders)
+                    self._root_vals[key] = op.get("value")
+                elif op["action"] == "del":
+                    self._root_vals.pop(key, None)
+                elif op["action"] in ("makeList", "makeMap"):
+                    self._root_vals[key] = [] if op["action"] == "makeList" else {}
             if op["action"] == "makeList":
                 if key == "text":
                     self._hist, self._hist_list = ArrivalHistory(), op["opId"]
@@ -125,15 +164,29 @@ class Micromerge:
                 pending.append(op)
         if not pending:
             return [p for kind, ps in out if kind == "root" for p in ps]
-        pos = {e[0]: k for k, e in enumerate(self._meta())}          # final positions (GPU materialisation or local mirror)
-        patches = []
+        device = None
+        if not local:
+            # remote changes: the device derived the patches of every op of the log while materialising it
+            batch, merged, dp = self._materialise()
+            if dp is not None and int(dp.status[0]) == 0:
+                lid = self._text_list_id()
+                log_ops = [op for ch in self._applied for op in ch["ops"]
+                           if op.get("obj") == lid and (op["action"] in ("addMark", "removeMark") or (op["action"] == "set" and op.get("insert")) or (op["action"] == "del" and op.get("key") is None))]
+                device = patch_stream(batch, dp, 0, log_ops)[len(log_ops) - len(pending):]
+        pos = None
+        patches, k = [], 0
         for kind, item in out:
             if kind == "root":
                 patches += item
             else:
                 op, t, emits = item
-                if emits:
+                if device is not None:
+                    patches += device[k]
+                elif emits:
+                    if pos is None:
+                        pos = {e[0]: j for j, e in enumerate(self._meta())}      # final positions (GPU materialisation or local mirror)
                     patches += derive_patch(op, t, pos, self._hist)
+                k += 1
         return patches
 
     # -- GPU materialisation --------------------------------------------------------------------------------------------
@@ -141,10 +194,16 @@ class Micromerge:
         return _root_text_list(self._applied)
 
     def _materialise(self):
+        """(packed log, merged result, device patches or None) — one device pass, cached until the log changes."""
         if self._cache is None:
             batch = pack_logs([self._applied])
             eng = self._engine or default_engine()
-            self._cache = (batch, eng.run(batch))
+            self.device_passes = getattr(self, "device_passes", 0) + 1
+            if getattr(eng, "emit_patches", False) and self._want_patches:
+                merged, dp = eng.run_with_patches(batch)
+                self._cache = (batch, merged, dp)
+            else:
+                self._cache = (batch, eng.run(batch), None)
         return self._cache
 
     def _meta(self):
@@ -152,7 +211,7 @@ class Micromerge:
         lid = self._text_list_id()
         if self._mirror is not None and self._mirror_list == lid:
             return self._mirror
-        batch, merged = self._materialise()
+        batch, merged, _ = self._materialise()
         if int(merged.results[0]["status"]) != 0:
             raise RangeError("List element not found")
         if merged.seq is None:
@@ -307,20 +366,20 @@ class Micromerge:
             raise RangeError(f"No object at path {list(path)!r}")
         if self._text_list_id() is None:
             raise JsError("Child not found: text in _root")          # :458
-        batch, merged = self._materialise()
+        batch, merged, _ = self._materialise()
         return decode_spans(batch, merged, 0)
 
     @property
     def root(self) -> dict:
         """`{text: [...visible values]}` (reference :290; fuzz.ts:33 and the tests read `root.text`)."""
         if self._text_list_id() is None:
-            return {}
+            return dict(self._root_vals)
         if self._mirror is not None and self._mirror_list == self._text_list_id():
-            return {"text": [e[3] for e in self._mirror if not e[1]]}
-        batch, merged = self._materialise()
+            return {**self._root_vals, "text": [e[3] for e in self._mirror if not e[1]]}
+        batch, merged, _ = self._materialise()
         if int(merged.results[0]["status"]) != 0:
             raise RangeError("List element not found")
-        return {"text": [token_str(int(t), batch.values) for t in merged.tokens(0)]}
+        return {**self._root_vals, "text": [token_str(int(t), batch.values) for t in merged.tokens(0)]}
 
     def getRoot(self) -> dict:
         return self.root

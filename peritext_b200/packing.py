@@ -431,3 +431,70 @@ def comment_pool_capacity(batch: PackedBatch) -> int:
     mk = batch.marks
     n_comment = int((((mk["kind"] >> 1) & 3) == 2).sum()) if len(mk) else 0
     return 64 * n_comment + 1024
+
+
+@dataclass
+class DevicePatches:
+    """The device Patch stream of a merged batch (include/peritext_b200.h pt_patch_view)."""
+    recs: np.ndarray      # PATCH_REC_DT per ins/del record (batch offsets)
+    items: np.ndarray     # PATCH_ITEM_DT pool entries, any order
+    status: np.ndarray    # per log: 0 computed on the device, 1 not computed (derive on the host)
+
+    def _index(self):
+        if not hasattr(self, "_by_log"):
+            by = {}
+            for it in self.items:
+                by.setdefault(int(it["log"]), []).append((int(it["tag"]), int(it["a"]), int(it["b"])))
+            self._by_log = by
+        return self._by_log
+
+
+def patch_stream(batch: PackedBatch, dp: DevicePatches, i: int, ops: Sequence[dict]) -> list[list[dict]]:
+    """Patches of log i as the reference's Patch objects (reference src/micromerge.ts:25-58), one list per list op of `ops`
+    (= the log's list ops in arrival order, the same ops `pack_logs` packed).  insert: {path, action, index, values, marks};
+    delete: {path, action, index, count: 1} (only the element's first delete emits); marks: {action, markType, path,
+    startIndex, [attrs], endIndex}."""
+    if int(dp.status[i]) != 0:
+        raise RangeError("patches of this log were not computed on the device")
+    d = batch.desc[i]
+    io = int(d["insdel_off"])
+    items = dp._index().get(i, [])
+    comments: dict[int, list[int]] = {}
+    mpatches: dict[int, list[tuple[int, int]]] = {}
+    for tag, a, b in items:
+        if tag & 0x80000000:
+            mpatches.setdefault(tag & 0x7FFFFFFF, []).append((a, b))
+        else:
+            comments.setdefault(tag, []).append(a)
+    out = []
+    ri = mi = 0
+    for op in ops:
+        act = op["action"]
+        if act in ("addMark", "removeMark"):
+            ps = []
+            for a, b in sorted(mpatches.get(mi, [])):
+                patch = {"action": act, "markType": op["markType"], "path": ["text"], "startIndex": a}
+                if act == "addMark" and op["markType"] in ("link", "comment"):
+                    patch["attrs"] = op["attrs"]
+                patch["endIndex"] = b
+                ps.append(patch)
+            out.append(ps); mi += 1
+            continue
+        r = dp.recs[io + ri]
+        idx, emits = int(r["index"]) & 0x7FFFFFFF, bool(int(r["index"]) >> 31)
+        if act == "set":
+            flags = int(r["flags"])
+            marks: dict[str, Any] = {}
+            if flags & SPAN_STRONG:
+                marks["strong"] = {"active": True}
+            if flags & SPAN_EM:
+                marks["em"] = {"active": True}
+            if flags & SPAN_COMMENT:
+                marks["comment"] = [batch.comment_ids[c] for c in sorted(comments.get(ri, []))]
+            if flags & SPAN_LINK:
+                marks["link"] = batch.link_attrs[int(r["link_attr"])]
+            out.append([{"path": ["text"], "action": "insert", "index": idx, "values": [op["value"]], "marks": marks}])
+        else:
+            out.append([{"path": ["text"], "action": "delete", "index": idx, "count": 1}] if emits else [])
+        ri += 1
+    return out

@@ -149,3 +149,44 @@ def test_reference_fuzz_loop_against_the_facade():
                         for k, op in enumerate(o for o in init["ops"] if o["action"] == "set")]
         for r in range(3):
             assert accumulatePatches(init_patches + all_patches[r]) == spans[r], (seed, r)
+
+
+@pytest.mark.gpu
+def test_apply_changes_bulk_is_one_device_pass_and_equals_the_oracle():
+    """`applyChanges` (causal retry as reference test/merge.ts:4-23): all patches of many changes from ONE device pass."""
+    from tests.harness import fuzz_session
+    _, logs, _ = fuzz_session(OracleMicromerge, 8100, 80, sync_prob=0.7)
+    log = logs[1]
+    f, o = Micromerge("observer"), OracleMicromerge("observer")
+    want = []
+    for ch in log:
+        want += o.applyChange(ch)
+    got = f.applyChanges(list(reversed(log)))            # worst arrival order: the queue sorts itself out causally
+    assert f.device_passes == 1
+    assert f.getTextWithFormatting(["text"]) == o.getTextWithFormatting(["text"]) and f.clock == o.clock
+    assert accumulatePatches(got) == accumulatePatches(want)
+    g = Micromerge("observer2")
+    assert g.applyChanges(log) == want and g.device_passes == 1          # same order: identical patch stream
+
+
+def test_facade_refuses_inserts_that_break_lamport_order_at_apply_time():
+    """An insert whose opId is not larger than its reference element's: the reference merges it, this engine cannot
+    (status PT_LOG_CYCLE); the facade says so at applyChange, before buffering (documented deviation)."""
+    from peritext_b200.packing import RangeError
+    from tests.harness import generateDocs
+    docs, _, init = generateDocs(OracleMicromerge, "abc", 1)
+    m = Micromerge("replica", patches=False)
+    m.applyChange(init)
+    bad = {"actor": "doc2", "seq": 1, "deps": {"doc1": 1}, "startOp": 2, "ops": [
+        {"opId": "2@doc2", "action": "set", "obj": "1@doc1", "elemId": "4@doc1", "insert": True, "value": "X"}]}
+    with pytest.raises(RangeError):
+        m.applyChange(bad)
+    assert m.clock == {"doc1": 1}                       # nothing was buffered
+
+
+def test_root_keeps_the_other_map_keys():
+    m = Micromerge("doc1", patches=False)
+    m.change([{"path": [], "action": "set", "key": "title", "value": "hi"}])
+    assert m.root == {"title": "hi"}
+    m.change([{"path": [], "action": "set", "key": "title", "value": "yo"}, {"path": [], "action": "set", "key": "n", "value": 3}])
+    assert m.root == {"title": "yo", "n": 3}
