@@ -191,6 +191,29 @@ def run_reference(args, rank, world):
     return 0
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """N > 1: pin this rank (and so its pinned staging buffers) to the CPU cores of its GPU's NUMA node; on an 8-GPU box
+    ranks that float across sockets contend for one socket's memory bandwidth on the host <-> device legs."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)], capture_output=True, text=True, timeout=10).stdout.strip()
+            bus = out.lower().replace("00000000:", "0000:")
+        else:
+            bus = "0000:%02x:00.0" % bus
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:      # topology files missing: run unbound
+        return {"error": str(e)[:80]}
+
+
 class DeviceRun:
     """One engine handle with a batch resident in HBM; `timed(steps)` = K merges (+ the digest all-gather on a side stream)."""
 
@@ -313,8 +336,10 @@ def main():
         return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        numa = bind_to_gpu_numa_node(torch, local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
     import __graft_entry__ as g
@@ -324,7 +349,7 @@ def main():
 
     cfg = workload.CONFIGS[args.config]
     n_docs_total = args.docs or (cfg["n_docs"] if args.config != "c5" else 16 * world)
-    gen_threads = max(1, (os.cpu_count() or 8) // world)
+    gen_threads = max(1, len(os.sched_getaffinity(0)) if world > 1 else (os.cpu_count() or 8))
 
     # ---- strong: the job's documents sharded by doc id over the ranks --------------------------------------------------
     first, count = sharding.shard_range(n_docs_total, rank, world)
@@ -461,7 +486,8 @@ def main():
                        "generator_s": round(gen_s, 2), "all_status_ok": ok, "replicas_converged": converged,
                        "docs_per_sec": total_logs / (ms_per_step / 1e3), "kernel_paths": stats,
                        "ms_per_step_min": per_step[0], "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_max": per_step[-1],
-                       "exchange": "none (1 rank)" if world == 1 else "all-gather of 32-byte result headers per step, side stream, inside the timed region"},
+                       "exchange": "none (1 rank)" if world == 1 else "all-gather of 32-byte result headers per step, side stream, inside the timed region",
+                       "rank0_cpu_binding": numa},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "ptk::merge_logs_warp_kernel" if warp_share else "ptk::merge_logs_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
