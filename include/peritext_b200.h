@@ -219,7 +219,8 @@ typedef struct pt_spans_view {
     uint64_t comment_pool_used;
     const uint32_t* seq;          /* NULL unless PT_FLAG_EMIT_SEQUENCE: per log (offset seq_off[i], n_elems entries) the element
                                      sequence incl. tombstones (the reference's `metadata` array, src/micromerge.ts:255):
-                                     bits30:0 = index of the element's insert record in the log's ins/del records,
+                                     bits29:0 = index of the element's insert record in the log's ins/del records,
+                                     bit30 = the element's markOpsAfter slot is defined (src/micromerge.ts:784),
                                      bit31 = deleted                                                                  */
     const uint64_t* seq_off;      /* [n_logs] offsets into seq (capacity layout: running sum of n_insdel); NULL without seq */
     uint64_t comment_pool_needed; /* comment-pool entries the whole batch needs; > the pool's capacity iff some logs
@@ -321,6 +322,17 @@ int pt_batch_download(pt_batch*, pt_spans_view* out);
  * memory, valid until the next upload / destroy). Synchronises. */
 int pt_batch_download_patches(pt_batch*, pt_patch_view* out);
 int pt_batch_set_patch_pool(pt_batch*, uint64_t items);
+
+/* Batched index -> element resolution on the materialised documents (PT_FLAG_EMIT_SEQUENCE, after a merge): what
+ * op generation and cursors need (getListElementId, src/micromerge.ts:762-805; getCursor :465).  Query k asks log
+ * `log` for its `index`-th visible element; with PT_QUERY_LOOK_AFTER_TOMBSTONES the answer moves to the LAST following
+ * tombstone whose markOpsAfter slot is defined (:775-797, the rule Micromerge.change uses for insert positions).
+ * Answers: index of the element's insert record in the log's ins/del records, PT_ELEM_NOT_FOUND if the index is out of
+ * bounds ("List index out of bounds", :804).  One warp per query on the device; synchronises. */
+typedef struct pt_elem_query { uint32_t log; uint32_t index; uint32_t flags; uint32_t reserved; } pt_elem_query;
+#define PT_QUERY_LOOK_AFTER_TOMBSTONES 1u
+#define PT_ELEM_NOT_FOUND 0xFFFFFFFFu
+int pt_batch_query_elements(pt_batch*, const pt_elem_query* queries, uint32_t n, uint32_t* record_index_out);
 
 /* Copy only the per-log result headers (status, counts, digest). Synchronises the stream. */
 int pt_batch_download_results(pt_batch*, pt_log_result* out, uint32_t n_logs);

@@ -291,6 +291,51 @@ __global__ void admit_kernel(const pt_change_desc* __restrict__ cd, const pt_cha
     }
 }
 
+
+// ---- batched getListElementId (reference src/micromerge.ts:762-805) over the materialised element sequences ----------------
+// One warp per query: ballot / popcount over the sequence words finds the k-th visible element; lookAfterTombstones then
+// scans the run of tombstones that follows for the last one whose markOpsAfter slot is defined (bit 30).
+__global__ void query_elements_kernel(const pt_elem_query* __restrict__ q, uint32_t n, const pt_log_result* __restrict__ res,
+                                      const uint64_t* __restrict__ seq_off, const uint32_t* __restrict__ seq, uint32_t n_logs, uint32_t* __restrict__ out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t k = warp; k < n; k += nwarps) {
+        const pt_elem_query Q = q[k];
+        uint32_t ans = PT_ELEM_NOT_FOUND;
+        if (Q.log < n_logs && res[Q.log].status == 0) {
+            const uint32_t N = res[Q.log].n_elems;
+            const uint32_t* s = seq + seq_off[Q.log];
+            uint32_t seen = 0, pos = 0xFFFFFFFFu;
+            for (uint32_t b = 0; b < N && pos == 0xFFFFFFFFu; b += 32) {
+                const uint32_t e = b + lane < N ? s[b + lane] : 0x80000000u;
+                const uint32_t vis = __ballot_sync(0xffffffffu, !(e >> 31));
+                const uint32_t c = __popc(vis);
+                if (seen + c > Q.index) {
+                    uint32_t m = vis;                                        // (index - seen)-th set bit
+                    for (uint32_t r = Q.index - seen; r; r--) m &= m - 1;
+                    pos = b + (__ffs(m) - 1);
+                }
+                seen += c;
+            }
+            if (pos != 0xFFFFFFFFu) {
+                uint32_t best = pos;
+                if (Q.flags & PT_QUERY_LOOK_AFTER_TOMBSTONES) {
+                    bool open = true;
+                    for (uint32_t b = pos + 1; b < N && open; b += 32) {
+                        const uint32_t e = b + lane < N ? s[b + lane] : 0u;      // past the end counts as "not a tombstone"
+                        const uint32_t live = __ballot_sync(0xffffffffu, !(e >> 31));
+                        const uint32_t upto = live ? ((1u << (__ffs(live) - 1)) - 1u) : 0xFFFFFFFFu;    // tombstones before the next visible element
+                        const uint32_t marked = __ballot_sync(0xffffffffu, (e >> 30) & 1u) & upto;
+                        if (marked) best = b + (31 - __clz(marked));
+                        open = live == 0;
+                    }
+                }
+                ans = s[best] & 0x3FFFFFFFu;
+            }
+        }
+        if (lane == 0) out[k] = ans;
+    }
+}
+
 }  // namespace
 
 struct pt_batch {
@@ -960,6 +1005,30 @@ int pt_batch_set_patch_pool(pt_batch* b, uint64_t items) {
         if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
         b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0;
     }
+    return PT_OK;
+}
+
+int pt_batch_query_elements(pt_batch* b, const pt_elem_query* queries, uint32_t n, uint32_t* out) {
+    if (!b || (n && (!queries || !out))) return PT_ERR_INVALID;
+    if (!b->merged) { g_last_error = "query before merge"; return PT_ERR_STATE; }
+    if (!(b->limits.flags & PT_FLAG_EMIT_SEQUENCE)) { g_last_error = "the handle was created without PT_FLAG_EMIT_SEQUENCE"; return PT_ERR_STATE; }
+    if (!n) return PT_OK;
+    PT_CUDA(cudaSetDevice(b->device));
+    DevBuf dq, da;
+    int rc;
+    if ((rc = dq.reserve((size_t)n * sizeof(pt_elem_query))) || (rc = da.reserve((size_t)n * 4))) { dq.release(); da.release(); return rc; }
+    cudaError_t e = cudaMemcpyAsync(dq.p, queries, (size_t)n * sizeof(pt_elem_query), cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) {
+        const uint32_t threads = 128, grid = (uint32_t)std::min<uint64_t>(((uint64_t)n * 32 + threads - 1) / threads, (uint64_t)b->num_sms * 16);
+        query_elements_kernel<<<grid, threads, 0, b->stream>>>((const pt_elem_query*)dq.p, n, (const pt_log_result*)b->d_results.p,
+                                                              (const uint64_t*)b->d_text_off.p, (const uint32_t*)b->d_seq.p, b->n_logs, (uint32_t*)da.p);
+        e = cudaGetLastError();
+        b->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, da.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    dq.release(); da.release();
+    if (e != cudaSuccess) { g_last_error = std::string("pt_batch_query_elements: ") + cudaGetErrorString(e); return PT_ERR_CUDA; }
     return PT_OK;
 }
 

@@ -54,7 +54,7 @@ struct BatchParams {
     uint32_t prefetch_next;               // CTA-per-log kernel: prefetch the next log's records into L2 while working on the current one
     uint32_t warp_flags;                  // warp-per-log kernel: bit0 prefetch this log's marks, bit1 the next log's records, bit2 phase-aligned warps
     uint32_t use_tma;                     // stage the record stream through shared memory with cp.async.bulk (shared-only path)
-    uint32_t* seq;                        // optional: element sequence output (record index | deleted << 31), text offsets
+    uint32_t* seq;                        // optional: element sequence output (record index | after-slot defined << 30 | deleted << 31), text offsets
     const uint32_t* admit;                // optional: per-log admission status (pre-pass); non-zero: the log is not merged
 };
 
@@ -700,11 +700,17 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
                 // the boundary element must have ARRIVED before the mark op: the reference's walk at apply time never matches
                 // an element that is inserted later (peritext.ts:236-241) — a missing start is a no-op, a missing end never ends
                 Idx j = T[keyOf(start_ctr, start_actor)];
-                if (j != NONE && (uint32_t)j < arrival) { ps = 2u * posOf(j) + sb; vs = visOf(j) + ((sb && isVis(j)) ? 1u : 0u); }
+                if (j != NONE && (uint32_t)j < arrival) {
+                    ps = 2u * posOf(j) + sb; vs = visOf(j) + ((sb && isVis(j)) ? 1u : 0u);
+                    if (seq_out && sb == PT_BOUND_AFTER) atomicOr(&seq_out[posOf(j)], 0x40000000u);    // the element's markOpsAfter slot is defined
+                }
             }
             if (eb <= PT_BOUND_AFTER && !badId(end_ctr, end_actor)) {
                 Idx j = T[keyOf(end_ctr, end_actor)];
-                if (j != NONE && (uint32_t)j < arrival) { pe = 2u * posOf(j) + eb; ve = visOf(j) + ((eb && isVis(j)) ? 1u : 0u); }
+                if (j != NONE && (uint32_t)j < arrival) {
+                    pe = 2u * posOf(j) + eb; ve = visOf(j) + ((eb && isVis(j)) ? 1u : 0u);
+                    if (seq_out && eb == PT_BOUND_AFTER) atomicOr(&seq_out[posOf(j)], 0x40000000u);    // (src/peritext.ts:239-241 writes the end slot whenever the walk reaches it)
+                }
             }
             uint32_t a = 0, b = 0;
             if (ps != NOSLOT) {

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(32) patch_logs_kernel(const PatchParams P) {
             const uint4 r = ld_rec(ins + i);
             if ((r.w >> 30) == PT_KIND_INSERT) T[keyOf(r.x, r.z & 0xFFFFu)] = (uint16_t)i;
         }
-        for (uint32_t p = lane; p < N; p += 32) { const uint32_t rec = seq[p] & 0x7FFFFFFFu; PosOf[rec] = (uint16_t)p; TIns[p] = (uint16_t)rec; }
+        for (uint32_t p = lane; p < N; p += 32) { const uint32_t rec = seq[p] & 0x3FFFFFFFu; PosOf[rec] = (uint16_t)p; TIns[p] = (uint16_t)rec; }
         __syncwarp();
         for (uint32_t i = lane; i < n; i += 32) {
             const uint4 r = ld_rec(ins + i);

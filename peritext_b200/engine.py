@@ -20,7 +20,7 @@ _lib = None
 EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_upload_runs", "pt_compress_runs", "pt_batch_adopt_device", "pt_batch_upload_changes",
            "pt_ingest_create", "pt_ingest_parse", "pt_ingest_packed", "pt_ingest_pool", "pt_ingest_error", "pt_ingest_destroy", "pt_batch_merge", "pt_batch_sync",
            "pt_batch_download", "pt_batch_download_begin", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count", "pt_batch_stats",
-           "pt_batch_last_merge_ms", "pt_batch_set_comment_pool", "pt_batch_download_patches", "pt_batch_set_patch_pool", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
+           "pt_batch_last_merge_ms", "pt_batch_set_comment_pool", "pt_batch_download_patches", "pt_batch_set_patch_pool", "pt_batch_query_elements", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
 
 
 class EngineError(RuntimeError):
@@ -110,6 +110,7 @@ class _PatchView(ctypes.Structure):
                 ("status", ctypes.c_void_p)]
 
 
+QUERY_DT = np.dtype([("log", "<u4"), ("index", "<u4"), ("flags", "<u4"), ("reserved", "<u4")])
 PATCH_REC_DT = np.dtype([("index", "<u4"), ("flags", "<u4"), ("link_attr", "<u4"), ("reserved", "<u4")])
 PATCH_ITEM_DT = np.dtype([("log", "<u4"), ("tag", "<u4"), ("a", "<u4"), ("b", "<u4")])
 FLAG_EMIT_SEQUENCE = 1
@@ -149,6 +150,7 @@ def load_library() -> ctypes.CDLL:
     L.pt_batch_set_comment_pool.argtypes = [vp, u64]
     L.pt_batch_download_patches.argtypes = [vp, vp]
     L.pt_batch_set_patch_pool.argtypes = [vp, u64]
+    L.pt_batch_query_elements.argtypes = [vp, vp, u32, vp]
     L.pt_batch_destroy.argtypes = [vp]; L.pt_batch_destroy.restype = None
     L.pt_strerror.argtypes = [ctypes.c_int]; L.pt_strerror.restype = ctypes.c_char_p
     L.pt_last_error.restype = ctypes.c_char_p
@@ -291,6 +293,18 @@ class BatchEngine:
             recs, items, status, needed = self.download_patches()
         from .packing import DevicePatches
         return out, DevicePatches(recs, items, status)
+
+    def query_elements(self, logs, indices, look_after_tombstones=False) -> np.ndarray:
+        """Batched getListElementId on the device (reference src/micromerge.ts:762-805): for query k the index of the insert
+        record of log `logs[k]`'s `indices[k]`-th visible element (with `look_after_tombstones`: moved to the last following
+        tombstone whose after-slot is defined, the rule `change()` uses for insert positions); 0xFFFFFFFF = out of bounds.
+        Needs emit_sequence and a completed merge."""
+        q = np.zeros(len(logs), QUERY_DT)
+        q["log"], q["index"] = logs, indices
+        q["flags"] = np.asarray(look_after_tombstones, dtype=np.uint32) if not np.isscalar(look_after_tombstones) else (1 if look_after_tombstones else 0)
+        out = np.zeros(len(q), np.uint32)
+        _check(self._L.pt_batch_query_elements(self._h, q.ctypes.data, len(q), out.ctypes.data), "pt_batch_query_elements")
+        return out
 
     def set_comment_pool(self, entries: int):
         _check(self._L.pt_batch_set_comment_pool(self._h, int(entries)), "pt_batch_set_comment_pool")

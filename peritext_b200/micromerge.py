@@ -78,8 +78,18 @@ class Micromerge:
 
     # -- reference src/micromerge.ts:499-514 --------------------------------------------------------------------------
     def applyChange(self, change: dict) -> list:
+        snap = (dict(self.clock), self._maxOp, dict(self._objects), len(self._applied), dict(self._root_keys), dict(self._root_vals),
+                copy.deepcopy(self._hist), self._hist_list)
         self._admit(change)
-        return self._patches_for(change["ops"], local=False)
+        try:
+            return self._patches_for(change["ops"], local=False)
+        except RangeError:
+            # e.g. "List element not found": the reference drops the rest of the failing change; this facade drops the whole
+            # change, so that the document stays usable (a log the engine rejects would poison every later materialisation)
+            self.clock, self._maxOp, self._objects, n, self._root_keys, self._root_vals, self._hist, self._hist_list = snap
+            del self._applied[n:]
+            self._cache = None; self._mirror = None
+            raise
 
     def applyChanges(self, changes: list) -> list:
         """Admit a list of changes with causal retry (a change whose dependencies are not there yet goes back to the end of
@@ -168,6 +178,9 @@ class Micromerge:
         if not local:
             # remote changes: the device derived the patches of every op of the log while materialising it
             batch, merged, dp = self._materialise()
+            if int(merged.results[0]["status"]) != 0:
+                from .packing import LOG_STATUS
+                raise RangeError(LOG_STATUS.get(int(merged.results[0]["status"]), "engine status %d" % int(merged.results[0]["status"])))
             if dp is not None and int(dp.status[0]) == 0:
                 lid = self._text_list_id()
                 log_ops = [op for ch in self._applied for op in ch["ops"]
@@ -219,18 +232,14 @@ class Micromerge:
         ins, _ = batch.log_slice(0)
         actors = batch.log_actors[0]
         cmap = batch.log_counters[0] if batch.log_counters else None     # dense counter rank -> original counter
-        after_defined = set()      # elements whose markOpsAfter slot is defined: some applied op ends `after` them (peritext.ts:239-241)
-        for ch in self._applied:
-            for op in ch["ops"]:
-                if op.get("obj") == lid and op["action"] in ("addMark", "removeMark") and op["end"]["type"] == "after":
-                    after_defined.add(op["end"]["elemId"])
         mirror = []
         for e in merged.sequence(0):
-            r = ins[int(e) & 0x7FFFFFFF]
+            r = ins[int(e) & 0x3FFFFFFF]
             ctr = int(r["ctr"]) if cmap is None else int(cmap[int(r["ctr"])])
             eid = f"{ctr}@{actors[int(r['actor'])]}"
             tok = int(r["payload"]) & 0x3FFFFFFF
-            mirror.append([eid, bool(int(e) >> 31), eid in after_defined, token_str(tok, batch.values)])
+            # bit 30: the element's markOpsAfter slot is defined (some applied op starts / ends `after` it, peritext.ts:239-241)
+            mirror.append([eid, bool(int(e) >> 31), bool((int(e) >> 30) & 1), token_str(tok, batch.values)])
         self._mirror, self._mirror_list = mirror, lid
         return mirror
 

@@ -190,3 +190,23 @@ def test_root_keeps_the_other_map_keys():
     assert m.root == {"title": "hi"}
     m.change([{"path": [], "action": "set", "key": "title", "value": "yo"}, {"path": [], "action": "set", "key": "n", "value": 3}])
     assert m.root == {"title": "yo", "n": 3}
+
+
+@pytest.mark.gpu
+def test_a_change_the_engine_rejects_is_rolled_back():
+    """A list op naming an unknown element: `applyChange` raises "List element not found" (reference src/micromerge.ts:752)
+    and the change is not kept — the document stays usable (round-1 advisor finding: it used to poison every later read)."""
+    from peritext_b200.packing import RangeError
+    from tests.harness import generateDocs
+    docs, _, init = generateDocs(OracleMicromerge, "abc", 1)
+    m = Micromerge("replica")
+    m.applyChange(init)
+    bad = {"actor": "doc2", "seq": 1, "deps": {"doc1": 1}, "startOp": 9, "ops": [
+        {"opId": "9@doc2", "action": "del", "obj": "1@doc1", "elemId": "77@doc9"}]}
+    with pytest.raises(RangeError):
+        m.applyChange(bad)
+    assert m.clock == {"doc1": 1}
+    assert m.getTextWithFormatting(["text"]) == [{"marks": {}, "text": "abc"}]
+    good = docs[0].change([{"path": ["text"], "action": "insert", "index": 3, "values": ["d"]}])["change"]
+    m.applyChange(good)
+    assert m.root["text"] == list("abcd")
