@@ -98,6 +98,7 @@ struct BlockCtx {
     uint32_t status;
     uint32_t work, work_next;
     uint32_t misc[4];
+    uint32_t dup_cnt;                   // occupied id-table entries (must equal the number of inserts)
     unsigned long long dig0, dig1;
     unsigned long long pool_base;
 };
@@ -248,7 +249,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     A.sm_cap = P.smem_arena_bytes; A.sm_used = 0;
     A.gm = P.slab + (unsigned long long)blockIdx.x * P.slab_bytes; A.gm_cap = P.slab_bytes; A.gm_used = 0; A.overflow = false;
 
-    if (tid == 0) { c.status = 0; c.misc[0] = 0; c.misc[2] = 0; c.misc[3] = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
+    if (tid == 0) { c.status = 0; c.misc[0] = 0; c.misc[2] = 0; c.misc[3] = 0; c.dup_cnt = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
 
     auto keyOf = [&](uint32_t ctr, uint32_t actor) -> uint32_t { return (ctr - 1u) * R + actor; };
     auto badId = [&](uint32_t ctr, uint32_t actor) -> bool { return ctr - 1u >= C || actor >= R; };
@@ -291,20 +292,26 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     //    reference, where applyOp throws "List element not found" otherwise (src/micromerge.ts:752).
     {
         const uint4 zero4 = make_uint4(0, 0, 0, 0xC0000000u);     // kind 3: neither insert nor delete
-        auto stepA = [&](uint32_t i, const uint4 r, const uint4 rp) -> bool {   // returns: record needs a table lookup in B
+        auto stepA = [&](uint32_t i, const uint4 r, const uint4 rp) -> uint32_t {   // returns bit0: record needs a table lookup in B, bit1: it is a valid insert
             const uint32_t ctr = r.x, actor = r.z & 0xFFFFu, ref_ctr = r.y, ref_actor = r.z >> 16, kind = r.w >> 30;
             bool isIns = false, valid = false;
             if (i < n) {
                 if (kind > 1u) fail(PT_LOG_BAD_KIND);
                 else if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
-                else { valid = true; if (kind == PT_KIND_INSERT) { isIns = true; T[keyOf(ctr, actor)] = (Idx)i; } }
+                else {
+                    valid = true;
+                    if (kind == PT_KIND_INSERT) {
+                        isIns = true;
+                        T[keyOf(ctr, actor)] = (Idx)i;
+                    }
+                }
             }
             // reference element == the insert at record i-1 ?
             bool cand = isIns && ref_ctr != 0 && ref_ctr == rp.x && ref_actor == (rp.z & 0xFFFFu) && (rp.w >> 30) == PT_KIND_INSERT;
             if (cand && keyOf(ref_ctr, ref_actor) >= keyOf(ctr, actor)) { fail(PT_LOG_CYCLE); cand = false; }
             const uint32_t insW = __ballot_sync(0xffffffffu, isIns), candW = __ballot_sync(0xffffffffu, cand);
             if (lane == 0 && i < n) { InsBits[i >> 5] = insW; HeadBits[i >> 5] = candW; }
-            return valid && !cand;
+            return ((valid && !cand) ? 1u : 0u) | (isIns ? 2u : 0u);
         };
         auto stepB = [&](uint32_t i, bool live, const uint4 r) {
             if (!live) return;
@@ -339,12 +346,12 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
                 uint4 p0 = zero4, p1 = zero4;
                 if (i0 < n) { if (tid > 0) p0 = st[tid - 1]; else if (i0 > 0) p0 = ld_rec(ins + i0 - 1); }
                 if (i1 < n) p1 = st[BLOCK + tid - 1];
-                const bool l0 = stepA(i0, r0, p0);
-                const bool l1 = stepA(i1, r1, p1);
+                const uint32_t l0 = stepA(i0, r0, p0);
+                const uint32_t l1 = stepA(i1, r1, p1);
                 __syncthreads();                                   // the chunk's ids are in T; everyone is done with buffer b
                 if (tid == 0 && k + 2 < nch) { fence_proxy_async(); issue(k + 2); }
-                stepB(i0, l0, r0);
-                stepB(i1, l1, r1);
+                stepB(i0, l0 & 1u, r0);
+                stepB(i1, l1 & 1u, r1);
             }
             A.sm_used = stage_mark;                                // release the stage
         } else
@@ -353,15 +360,32 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             const uint4 r0 = i0 < n ? ld_rec(ins + i0) : zero4, r1 = i1 < n ? ld_rec(ins + i1) : zero4;
             // the left neighbours (same cache lines, L1 hits)
             const uint4 p0 = (i0 > 0 && i0 < n) ? ld_rec(ins + i0 - 1) : zero4, p1 = i1 < n ? ld_rec(ins + i1 - 1) : zero4;
-            const bool l0 = stepA(i0, r0, p0);
-            const bool l1 = stepA(i1, r1, p1);
+            const uint32_t l0 = stepA(i0, r0, p0);
+            const uint32_t l1 = stepA(i1, r1, p1);
             __syncthreads();                                       // the trip's ids are in T
-            stepB(i0, l0, r0);
-            stepB(i1, l1, r1);
+            stepB(i0, l0 & 1u, r0);
+            stepB(i1, l1 & 1u, r1);
         }
     }
     __syncthreads();
     if (c.status) { bail(); return 0; }
+    {   // two inserts with one opId leave ONE table entry: the number of occupied entries must equal the number of inserts
+        // (checked after phase C); a vectorised count over the table instead of a second look at every insert
+        const uint32_t nvec = (uint32_t)((KS * sizeof(Idx) + 15u) >> 4);
+        const uint4* tv = reinterpret_cast<const uint4*>(T);
+        uint32_t occ = 0;
+        for (uint32_t v = tid; v < nvec; v += BLOCK) {
+            const uint4 q = tv[v];
+            if (sizeof(Idx) == 2) {
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) occ += ((w[k] & 0xFFFFu) != 0xFFFFu) + ((w[k] >> 16) != 0xFFFFu);
+            } else occ += (q.x != 0xFFFFFFFFu) + (q.y != 0xFFFFFFFFu) + (q.z != 0xFFFFFFFFu) + (q.w != 0xFFFFFFFFu);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
+        if (lane == 0 && occ) atomicAdd(&c.dup_cnt, occ);
+    }
 
     // ---- C: runs, bit-parallel: head = insert & (!chain-link | predecessor has another child); visible = insert & !deleted
     uint32_t M, nvis;
@@ -395,6 +419,7 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     }
     __syncthreads();
     N = c.misc[0];
+    if (c.dup_cnt != N) { __syncthreads(); if (tid == 0) c.status = PT_LOG_BAD_OPID; __syncthreads(); bail(); return 0; }
     const uint32_t McBound = c.misc[2];
     if (2ull * M + 4 >= (1ull << kNodeNxtBits) || N >= (1u << 22)) { if (tid == 0) c.status = PT_LOG_OVERFLOW; __syncthreads(); bail(); return 0; }
 
@@ -603,27 +628,26 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
     auto visOf = [&](uint32_t i) -> uint32_t { return VisBase[runOf(i)] + visBefore(i); };         // visible elements before it in the sequence
     auto isVis = [&](uint32_t i) -> bool { return (VisBits[i >> 5] >> (i & 31)) & 1u; };
 
-    // ---- F: text out (visible index = prefix count of non-deleted elements, micromerge.ts:747-750) + duplicate-id check --
+    // ---- F: text out (visible index = prefix count of non-deleted elements, micromerge.ts:747-750) ------------------------------
+    // only VISIBLE elements are touched (4 bytes of their record: the value token); the element sequence, when requested,
+    // needs every insert
     {
         unsigned long long d0 = 0, d1 = 0;
-        auto stepF = [&](uint32_t i, bool live, const uint4 r) {
+        auto stepF = [&](uint32_t i, bool live) {
             if (!live) return;
-            if ((uint32_t)T[keyOf(r.x, r.z & 0xFFFFu)] != i) fail(PT_LOG_BAD_OPID);     // two inserts with one opId
-            if (seq_out) seq_out[posOf(i)] = i | (isVis(i) ? 0u : 0x80000000u);
-            if (!isVis(i)) return;
-            const uint32_t tok = PT_PAYLOAD_TOKEN(r.w);
+            const bool vis = isVis(i);
+            if (seq_out) seq_out[posOf(i)] = i | (vis ? 0u : 0x80000000u);
+            if (!vis) return;
+            const uint32_t tok = PT_PAYLOAD_TOKEN(__ldg(&ins[i].payload));
             const uint32_t vr = visOf(i);
             text_out[vr] = tok;
             digest_add(d0, d1, pt_term_text(vr, tok));
         };
+        const uint32_t* LiveBits = seq_out ? InsBits : VisBits;
         for (uint32_t base = 0; base < n; base += 2 * BLOCK) {
             const uint32_t i0 = base + tid, i1 = i0 + BLOCK;
-            const bool l0 = i0 < n && ((InsBits[i0 >> 5] >> (i0 & 31)) & 1u), l1 = i1 < n && ((InsBits[i1 >> 5] >> (i1 & 31)) & 1u);
-            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-            if (l0) r0 = ld_rec(ins + i0);
-            if (l1) r1 = ld_rec(ins + i1);
-            stepF(i0, l0, r0);
-            stepF(i1, l1, r1);
+            stepF(i0, i0 < n && ((LiveBits[i0 >> 5] >> (i0 & 31)) & 1u));
+            stepF(i1, i1 < n && ((LiveBits[i1 >> 5] >> (i1 & 31)) & 1u));
         }
         digest_flush<BLOCK>(c, d0, d1);
     }

@@ -48,17 +48,18 @@ struct WArena {
 // barriers at a few phase boundaries keep the warps of a CTA in the same code region.  A warp that leaves a log early
 // (error status, deferral, no work) ARRIVES at the remaining barriers without waiting, so nobody waits for it.
 constexpr uint32_t kFirstPhaseBar = 2, kLastPhaseBar = 5;      // barrier 1 = start of a round (work loop)
-__device__ __noinline__ void phase_arrive_rest(uint32_t next, uint32_t nthreads) {
-    for (; next <= kLastPhaseBar; next++) asm volatile("barrier.arrive %0, %1;" ::"r"(next), "r"(nthreads) : "memory");
+__device__ __noinline__ void phase_arrive_rest(uint32_t next, uint32_t nthreads, uint32_t skip) {
+    for (; next <= kLastPhaseBar; next++)
+        if (!((skip >> (next - kFirstPhaseBar)) & 1u)) asm volatile("barrier.arrive %0, %1;" ::"r"(next), "r"(nthreads) : "memory");
 }
 struct PhaseSync {
-    uint32_t on, nthreads, next;
+    uint32_t on, nthreads, next, skip;      // skip: bit k set = phase barrier kFirstPhaseBar + k is not used (tuning)
     __device__ __forceinline__ void pass() {
-        if (on) asm volatile("barrier.sync %0, %1;" ::"r"(next), "r"(nthreads) : "memory");
+        if (on && !((skip >> (next - kFirstPhaseBar)) & 1u)) asm volatile("barrier.sync %0, %1;" ::"r"(next), "r"(nthreads) : "memory");
         next++;
     }
     __device__ __forceinline__ void leave() {
-        if (on && next <= kLastPhaseBar) phase_arrive_rest(next, nthreads);
+        if (on && next <= kLastPhaseBar) phase_arrive_rest(next, nthreads, skip);
         next = kLastPhaseBar + 1;
     }
 };
@@ -784,7 +785,7 @@ __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 
     uint32_t done = 0, deferred = 0;
     const bool phased = (P.warp_flags & 4u) != 0;
     __shared__ uint32_t s_base[2];
-    PhaseSync ps; ps.on = phased ? 1u : 0u; ps.nthreads = WARPS * 32; ps.next = kFirstPhaseBar;
+    PhaseSync ps; ps.on = phased ? 1u : 0u; ps.nthreads = WARPS * 32; ps.next = kFirstPhaseBar; ps.skip = (P.warp_flags >> 8) & 0xFu;
     uint32_t nextb = 0, par = 0;           // phased: the CTA's next round (held by thread 0)
     uint32_t w = 0, wend = 0, wn = 0;      // free: this warp's current grab [w, wend) and the next one
     if (phased) { if (threadIdx.x == 0) nextb = atomicAdd(P.work_counter, (uint32_t)WARPS); }

@@ -167,3 +167,27 @@ def test_marks_heavy_log_above_32000_records(engine):
     got = engine.run(batch)
     ref, _ = replay_packed(batch, threads=2)
     assert_equal(batch, got, ref)
+
+
+def test_duplicate_insert_opids_are_reported_by_both_kernels():
+    # two inserts with one (fresh, unreferenced) opId appended to a log — adjacent, and separated by another insert:
+    # PT_LOG_BAD_OPID from the warp kernel (caught at write time) and from the CTA kernel (id-table occupancy count);
+    # the other logs of the batch are unaffected
+    from peritext_b200.packing import DESC_DT, INSDEL_DT, PackedBatch
+    batch = workload.generate("c2", n_docs=3, ops_per_doc=1500)
+    extra = {0: [1, 1], 3: [1, 2, 1]}            # log -> counters (relative to max_ctr) of the appended HEAD inserts
+    parts, desc, off = [], batch.desc.copy(), 0
+    for i in range(batch.n_logs):
+        ins, _ = batch.log_slice(i)
+        add = np.zeros(len(extra.get(i, [])), INSDEL_DT)
+        for k, c in enumerate(extra.get(i, [])):
+            add[k] = (int(desc[i]["max_ctr"]) + c, 0, 0, 0, ord("x"))
+        parts += [ins, add]
+        desc[i]["insdel_off"] = off
+        desc[i]["n_insdel"] = len(ins) + len(add)
+        desc[i]["max_ctr"] = int(desc[i]["max_ctr"]) + 2
+        off += len(ins) + len(add)
+    bad = PackedBatch(desc, np.concatenate(parts), batch.marks, meta=dict(batch.meta))
+    for env in (None, "0"):
+        got, _ = run_with(env, bad)
+        assert got.results["status"].tolist() == [2, 0, 0, 2, 0, 0], env

@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT
+timeout 1800 python -m pytest tests/test_gpu_parity.py tests/test_gpu_adversarial.py tests/test_gpu_workloads.py tests/test_gpu_round2.py -m gpu -x -q -k "not c5" 2>&1 | tail -5
+for c in c2 c3; do echo "== $c"; timeout 600 python bench.py --config $c --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --no-extras 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],4), round(d['roofline']['frac'],4), d['config']['all_status_ok'])"; done
