@@ -153,6 +153,31 @@ typedef struct pt_change_table {
     uint64_t n_deps_total;
 } pt_change_table;
 
+/* ------------------------------------------------------------------------------------------------
+ * Compact wire format (optional, for the host -> device leg): the same records in half the bytes.
+ * Usable for a log with max_ctr < 65536, n_insdel < 65536 and n_actors <= 16 (any document the
+ * benchmark shapes produce); value tokens must fit 22 bits (any Unicode code point, or a value-pool
+ * index < 2^21).  Records keep their positions (the descriptors are those of the expanded layout);
+ * pt_batch_upload_compact expands them to pt_insdel_rec / pt_mark_rec on the device, elementwise.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_insdel_c8 {   /* 8 B */
+    uint16_t ctr, ref_ctr;
+    uint32_t w;                 /* bits3:0 actor, 7:4 ref_actor, 9:8 kind, 31:10 token (bit21 of the token = value-pool flag) */
+} pt_insdel_c8;
+typedef struct pt_mark_c16 {    /* 16 B */
+    uint16_t ctr, start_ctr, end_ctr, arrival;
+    uint32_t attr;
+    uint32_t w;                 /* bits3:0 actor, 7:4 start_actor, 11:8 end_actor, 14:12 kind, 18:15 bounds */
+} pt_mark_c16;
+typedef struct pt_packed_compact {
+    uint32_t n_logs;
+    const pt_log_desc* logs;       /* the EXPANDED layout */
+    const pt_insdel_c8* insdel;    /* [n_insdel_total] */
+    uint64_t n_insdel_total;
+    const pt_mark_c16* marks;      /* [n_mark_total] */
+    uint64_t n_mark_total;
+} pt_packed_compact;
+
 /* A host-side batch of logs (SoA). */
 typedef struct pt_packed_ops {
     uint32_t n_logs;
@@ -299,6 +324,13 @@ int pt_compress_runs(const pt_packed_ops* ops, uint64_t* run_off, uint64_t* tok_
  * PT_LOG_MISSING_DEP and are skipped by the merge (the reference throws before mutating, src/micromerge.ts:501-509).
  * Call after pt_batch_upload*; a new upload drops the table. */
 int pt_batch_upload_changes(pt_batch*, const pt_change_table* host_changes);
+
+/* Host helper (multithreaded): convert a packed batch to the compact wire format into caller-provided arrays of
+ * n_insdel_total / n_mark_total entries.  PT_ERR_INVALID (nothing useful written) if some log is not representable. */
+int pt_compact_ops(const pt_packed_ops* ops, pt_insdel_c8* insdel_out, pt_mark_c16* marks_out, int threads /* 0 = all cores */);
+
+/* Same as pt_batch_upload for the compact form: half the bytes over PCIe, expanded on the device (two elementwise kernels). */
+int pt_batch_upload_compact(pt_batch*, const pt_packed_compact* host_compact);
 
 /* Adopt a batch that is ALREADY RESIDENT in device memory (pointers are device pointers owned by the
  * caller, e.g. torch tensors); only the descriptors are read on the host. */

@@ -4,10 +4,12 @@
 // by size (block size + shared-memory budget per bin), order each bin largest-first for the persistent-CTA work
 // queue, launch, and move results.  There is NO CPU fallback: without a CUDA device every entry point fails.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "merge_kernel.cuh"
@@ -139,6 +141,32 @@ __global__ void expand_runs_kernel(const pt_log_desc* __restrict__ desc, const u
     }
 }
 
+
+// ---- compact wire format: elementwise expansion to the 16 / 32 byte records the merge kernels read -------------------------
+__global__ void expand_insdel_c8_kernel(const pt_insdel_c8* __restrict__ in, pt_insdel_rec* __restrict__ out, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(in + i));
+        const uint32_t tok22 = q.y >> 10;
+        uint4 o;
+        o.x = q.x & 0xFFFFu; o.y = q.x >> 16;
+        o.z = (q.y & 0xFu) | (((q.y >> 4) & 0xFu) << 16);
+        o.w = (((q.y >> 8) & 3u) << 30) | ((tok22 & 0x200000u) ? PT_TOKEN_POOLED : 0u) | (tok22 & 0x1FFFFFu);
+        reinterpret_cast<uint4*>(out)[i] = o;
+    }
+}
+__global__ void expand_mark_c16_kernel(const pt_mark_c16* __restrict__ in, pt_mark_rec* __restrict__ out, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + i));
+        // pt_mark_rec: {ctr, actor | kind << 16 | bounds << 24, start_ctr, end_ctr} {start_actor | end_actor << 16, attr, arrival, 0}
+        uint4 a, b;
+        a.x = q.x & 0xFFFFu;
+        a.y = (q.w & 0xFu) | (((q.w >> 12) & 7u) << 16) | (((q.w >> 15) & 0xFu) << 24);
+        a.z = q.x >> 16; a.w = q.y & 0xFFFFu;
+        b.x = ((q.w >> 4) & 0xFu) | (((q.w >> 8) & 0xFu) << 16);
+        b.y = q.z; b.z = q.y >> 16; b.w = 0;
+        reinterpret_cast<uint4*>(out)[2 * i] = a; reinterpret_cast<uint4*>(out)[2 * i + 1] = b;
+    }
+}
 
 // ---- output compaction (download path) ---------------------------------------------------------------------------------
 // The merge kernels write each log's tokens / spans at offsets derived from the descriptors alone (capacity = n_insdel
@@ -355,7 +383,7 @@ struct pt_batch {
     size_t bin_slab[kNumBins] = {0};
     size_t retry_slab = 0;
     // device
-    DevBuf d_runs, d_tokens, d_run_off, d_tok_off;
+    DevBuf d_runs, d_tokens, d_run_off, d_tok_off, d_cins, d_cmarks;
     DevBuf d_desc, d_insdel, d_marks, d_order, d_counters, d_results, d_text_off, d_span_off, d_text, d_spans, d_pool, d_slab, d_retry, d_seq;
     DevBuf d_bsum, d_ctoff, d_csoff, d_ctext, d_cspans;   // download path: packed outputs + their offsets ([n_logs + 1])
     DevBuf d_cdesc, d_changes, d_deps, d_admit;           // admission pre-pass (optional change table)
@@ -746,6 +774,81 @@ int pt_compress_runs(const pt_packed_ops* ops, uint64_t* run_off, uint64_t* tok_
 }
 int pt_batch_adopt_device(pt_batch* b, const pt_packed_ops* ops) { return upload_common(b, ops, true); }
 
+int pt_compact_ops(const pt_packed_ops* ops, pt_insdel_c8* io, pt_mark_c16* mo, int threads) {
+    if (!ops || (ops->n_insdel_total && !io) || (ops->n_mark_total && !mo)) return PT_ERR_INVALID;
+    for (uint32_t i = 0; i < ops->n_logs; i++) {
+        const pt_log_desc& L = ops->logs[i];
+        if (L.max_ctr >= 65536u || L.n_insdel >= 65536u || L.n_actors > 16u) { g_last_error = "log not representable in the compact wire format"; return PT_ERR_INVALID; }
+    }
+    int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<int> bad{0};
+    auto work = [&](int t) {
+        const uint64_t n = ops->n_insdel_total, a = n * t / T, b2 = n * (t + 1) / T;
+        for (uint64_t k = a; k < b2; k++) {
+            const pt_insdel_rec& r = ops->insdel[k];
+            const uint32_t tok = PT_PAYLOAD_TOKEN(r.payload), val = tok & (PT_TOKEN_POOLED - 1);
+            if (val >= 0x200000u) bad = 1;
+            pt_insdel_c8 o; o.ctr = (uint16_t)r.ctr; o.ref_ctr = (uint16_t)r.ref_ctr;
+            o.w = (r.actor & 0xFu) | ((r.ref_actor & 0xFu) << 4) | (PT_PAYLOAD_KIND(r.payload) << 8) | (((tok & PT_TOKEN_POOLED ? 0x200000u : 0u) | (val & 0x1FFFFFu)) << 10);
+            io[k] = o;
+        }
+        const uint64_t m = ops->n_mark_total, c = m * t / T, d = m * (t + 1) / T;
+        for (uint64_t k = c; k < d; k++) {
+            const pt_mark_rec& r = ops->marks[k];
+            if (r.arrival >= 65536u) bad = 1;
+            pt_mark_c16 o; o.ctr = (uint16_t)r.ctr; o.start_ctr = (uint16_t)r.start_ctr; o.end_ctr = (uint16_t)r.end_ctr; o.arrival = (uint16_t)r.arrival; o.attr = r.attr;
+            o.w = (r.actor & 0xFu) | ((r.start_actor & 0xFu) << 4) | ((r.end_actor & 0xFu) << 8) | ((r.kind & 7u) << 12) | ((r.bounds & 0xFu) << 15);
+            mo[k] = o;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    if (bad) { g_last_error = "value token or arrival index not representable in the compact wire format"; return PT_ERR_INVALID; }
+    return PT_OK;
+}
+
+int pt_batch_upload_compact(pt_batch* b, const pt_packed_compact* cc) {
+    if (!b || !cc || (cc->n_logs && !cc->logs)) return PT_ERR_INVALID;
+    PT_CUDA(cudaSetDevice(b->device));
+    PT_CUDA(cudaStreamSynchronize(b->stream));
+    b->have_batch = false; b->merged = false;
+    if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
+    b->graph_ok = false; b->graph_tried = false; b->merges_since_upload = 0; b->dl_begun = false; b->have_changes = false;
+    pt_packed_ops ops{cc->n_logs, cc->logs, nullptr, cc->n_insdel_total, nullptr, cc->n_mark_total};
+    int rc = plan_batch(b, &ops);
+    if (rc) return rc;
+    if ((rc = alloc_and_upload_plan(b))) return rc;
+    if ((rc = b->d_insdel.reserve(std::max<uint64_t>(1, b->n_insdel) * sizeof(pt_insdel_rec)))) return rc;
+    if ((rc = b->d_marks.reserve(std::max<uint64_t>(1, b->n_mark) * sizeof(pt_mark_rec)))) return rc;
+    if ((rc = b->d_cins.reserve(std::max<uint64_t>(1, b->n_insdel) * sizeof(pt_insdel_c8)))) return rc;
+    if ((rc = b->d_cmarks.reserve(std::max<uint64_t>(1, b->n_mark) * sizeof(pt_mark_c16)))) return rc;
+    const uint32_t threads = 256, gmax = (uint32_t)b->num_sms * 16;
+    if (b->n_insdel) {
+        PT_CUDA(cudaMemcpyAsync(b->d_cins.p, cc->insdel, b->n_insdel * sizeof(pt_insdel_c8), cudaMemcpyHostToDevice, b->stream));
+        expand_insdel_c8_kernel<<<(uint32_t)std::min<uint64_t>((b->n_insdel + threads - 1) / threads, gmax), threads, 0, b->stream>>>(
+            (const pt_insdel_c8*)b->d_cins.p, (pt_insdel_rec*)b->d_insdel.p, b->n_insdel);
+        b->launches++;
+    }
+    if (b->n_mark) {
+        PT_CUDA(cudaMemcpyAsync(b->d_cmarks.p, cc->marks, b->n_mark * sizeof(pt_mark_c16), cudaMemcpyHostToDevice, b->stream));
+        expand_mark_c16_kernel<<<(uint32_t)std::min<uint64_t>((b->n_mark + threads - 1) / threads, gmax), threads, 0, b->stream>>>(
+            (const pt_mark_c16*)b->d_cmarks.p, (pt_mark_rec*)b->d_marks.p, b->n_mark);
+        b->launches++;
+    }
+    PT_CUDA(cudaGetLastError());
+    b->dp_insdel = (const pt_insdel_rec*)b->d_insdel.p; b->dp_marks = (const pt_mark_rec*)b->d_marks.p; b->adopted = false;
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    if (!((b->n_insdel == 0 || pinned(cc->insdel)) && (b->n_mark == 0 || pinned(cc->marks)))) PT_CUDA(cudaStreamSynchronize(b->stream));
+    b->have_batch = true;
+    return PT_OK;
+}
+
 int pt_batch_upload_changes(pt_batch* b, const pt_change_table* t) {
     if (!b || !t) return PT_ERR_INVALID;
     if (!b->have_batch) { g_last_error = "pt_batch_upload_changes before pt_batch_upload"; return PT_ERR_STATE; }
@@ -1077,7 +1180,7 @@ void pt_batch_destroy(pt_batch* b) {
     cudaStreamSynchronize(b->stream);
     for (DevBuf* d : {&b->d_desc, &b->d_insdel, &b->d_marks, &b->d_order, &b->d_counters, &b->d_results, &b->d_text_off,
                       &b->d_span_off, &b->d_text, &b->d_spans, &b->d_pool, &b->d_slab, &b->d_retry, &b->d_seq,
-                      &b->d_runs, &b->d_tokens, &b->d_run_off, &b->d_tok_off, &b->d_bsum, &b->d_ctoff, &b->d_csoff, &b->d_ctext, &b->d_cspans,
+                      &b->d_runs, &b->d_tokens, &b->d_run_off, &b->d_tok_off, &b->d_cins, &b->d_cmarks, &b->d_bsum, &b->d_ctoff, &b->d_csoff, &b->d_ctext, &b->d_cspans,
                       &b->d_cdesc, &b->d_changes, &b->d_deps, &b->d_admit, &b->d_patch_recs, &b->d_patch_items, &b->d_patch_status}) d->release();
     for (HostBuf* h : {&b->h_patch_recs, &b->h_patch_items, &b->h_patch_status, &b->h_patch_misc}) h->release();
     for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc, &b->h_seq, &b->h_ctoff, &b->h_csoff}) h->release();

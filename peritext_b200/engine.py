@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libperitext_b200.so")
 _lib = None
 
-EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_upload_runs", "pt_compress_runs", "pt_batch_adopt_device", "pt_batch_upload_changes",
+EXPORTS = ["pt_batch_create", "pt_batch_upload", "pt_batch_upload_runs", "pt_compress_runs", "pt_compact_ops", "pt_batch_upload_compact", "pt_batch_adopt_device", "pt_batch_upload_changes",
            "pt_ingest_create", "pt_ingest_parse", "pt_ingest_packed", "pt_ingest_pool", "pt_ingest_error", "pt_ingest_destroy", "pt_batch_merge", "pt_batch_sync",
            "pt_batch_download", "pt_batch_download_begin", "pt_batch_download_results", "pt_batch_device_results", "pt_batch_launch_count", "pt_batch_stats",
            "pt_batch_last_merge_ms", "pt_batch_set_comment_pool", "pt_batch_download_patches", "pt_batch_set_patch_pool", "pt_batch_query_elements", "pt_batch_destroy", "pt_strerror", "pt_last_error", "pt_version"]
@@ -38,6 +38,8 @@ class _PackedRuns(ctypes.Structure):
                 ("n_insdel_total", ctypes.c_uint64), ("n_mark_total", ctypes.c_uint64)]
 
 
+INSDEL_C8_DT = np.dtype([("ctr", "<u2"), ("ref_ctr", "<u2"), ("w", "<u4")])
+MARK_C16_DT = np.dtype([("ctr", "<u2"), ("start_ctr", "<u2"), ("end_ctr", "<u2"), ("arrival", "<u2"), ("attr", "<u4"), ("w", "<u4")])
 RUN_DT = np.dtype([("ctr0", "<u4"), ("ref_ctr", "<u4"), ("actor", "<u2"), ("ref_actor", "<u2"), ("kind_count", "<u4")])
 
 
@@ -132,6 +134,8 @@ def load_library() -> ctypes.CDLL:
     L.pt_batch_upload_runs.argtypes = [vp, vp]
     L.pt_compress_runs.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.pt_batch_upload_changes.argtypes = [vp, vp]
+    L.pt_compact_ops.argtypes = [vp, vp, vp, ctypes.c_int]
+    L.pt_batch_upload_compact.argtypes = [vp, vp]
     L.pt_ingest_create.argtypes = [ctypes.POINTER(vp)]
     L.pt_ingest_parse.argtypes = [vp, vp, vp, u32, ctypes.c_int]
     L.pt_ingest_packed.argtypes = [vp, vp, vp]
@@ -198,6 +202,23 @@ class BatchEngine:
         d, c, p = np.ascontiguousarray(table.desc), np.ascontiguousarray(table.changes), np.ascontiguousarray(table.deps)
         t = _ChangeTable(len(d), d.ctypes.data, c.ctypes.data if len(c) else 0, len(c), p.ctypes.data if len(p) else 0, len(p))
         _check(self._L.pt_batch_upload_changes(self._h, ctypes.byref(t)), "pt_batch_upload_changes")
+
+    def upload_compact(self, batch: PackedBatch, cins: np.ndarray | None = None, cmarks: np.ndarray | None = None, threads: int = 0):
+        """Upload in the compact wire format (8-byte ins/del, 16-byte mark records; expanded on the device): the conversion
+        (pt_compact_ops, multithreaded) writes into `cins` / `cmarks` (INSDEL_C8_DT / MARK_C16_DT arrays, ideally pinned)."""
+        desc = np.ascontiguousarray(batch.desc)
+        insdel = np.ascontiguousarray(batch.insdel); marks = np.ascontiguousarray(batch.marks)
+        if cins is None:
+            cins = np.zeros(max(1, len(insdel)), INSDEL_C8_DT)
+        if cmarks is None:
+            cmarks = np.zeros(max(1, len(marks)), MARK_C16_DT)
+        ops = self._ops_struct(desc, insdel.ctypes.data, len(insdel), marks.ctypes.data, len(marks))
+        _check(self._L.pt_compact_ops(ctypes.byref(ops), cins.ctypes.data, cmarks.ctypes.data, threads), "pt_compact_ops")
+        cc = _PackedOps(len(desc), desc.ctypes.data, cins.ctypes.data, len(insdel), cmarks.ctypes.data, len(marks))     # same field layout as pt_packed_compact
+        self._keep = (desc, cins, cmarks)
+        _check(self._L.pt_batch_upload_compact(self._h, ctypes.byref(cc)), "pt_batch_upload_compact")
+        self.n_logs = len(desc)
+        self._n_insdel = len(insdel)
 
     def upload_runs(self, r: PackedRuns):
         desc = np.ascontiguousarray(r.desc)
@@ -347,8 +368,21 @@ class PipelinedEngine:
             self._streams = [torch.cuda.Stream(device=device) for _ in range(chunks)]
         self.engines = [BatchEngine(device, stream=s.cuda_stream) for s in self._streams]
 
-    def run(self, batch, copy: bool = False) -> list[MergedBatch]:
-        """`batch`: a PackedBatch, or a PackedRuns (run-compressed upload)."""
+    def _compact_buffers(self, k: int, n_ins: int, n_mk: int):
+        """Pinned conversion targets of chunk k (allocated once, grown on demand)."""
+        import torch
+        if not hasattr(self, "_cbuf"):
+            self._cbuf = {}
+        cur = self._cbuf.get(k)
+        if cur is None or cur[0].numel() < n_ins * 8 or cur[1].numel() < n_mk * 16:
+            cur = (torch.empty(max(16, n_ins * 8 + n_ins), dtype=torch.uint8).pin_memory(), torch.empty(max(16, n_mk * 16 + n_mk), dtype=torch.uint8).pin_memory())
+            self._cbuf[k] = cur
+        return cur[0].numpy()[: n_ins * 8].view(INSDEL_C8_DT), cur[1].numpy()[: n_mk * 16].view(MARK_C16_DT)
+
+    def run(self, batch, copy: bool = False, compact: bool = False, threads: int = 0) -> list[MergedBatch]:
+        """`batch`: a PackedBatch, or a PackedRuns (run-compressed upload).  `compact`: convert every chunk to the compact wire
+        format on the host (multithreaded, inside this call) and upload half the bytes; chunk k+1's conversion overlaps
+        chunk k's transfer."""
         n = batch.n_logs
         # cut by records, not by log count, so the chunks carry similar work
         w = np.cumsum(batch.desc["n_insdel"].astype(np.int64) + 2 * batch.desc["n_mark"].astype(np.int64))
@@ -359,6 +393,9 @@ class PipelinedEngine:
         for e, sb in zip(used, subs):
             if isinstance(sb, PackedRuns):
                 e.upload_runs(sb)
+            elif compact:
+                ci, cm = self._compact_buffers(used.index(e), len(sb.insdel), len(sb.marks))
+                e.upload_compact(sb, ci, cm, threads)
             else:
                 e.upload(sb)
             e.merge(); e.download_begin()

@@ -191,3 +191,21 @@ def test_duplicate_insert_opids_are_reported_by_both_kernels():
     for env in (None, "0"):
         got, _ = run_with(env, bad)
         assert got.results["status"].tolist() == [2, 0, 0, 2, 0, 0], env
+
+
+@pytest.mark.parametrize("cfg,n_docs,ops", [("c4", 120, 1000), ("c3", 6, 6000)])
+def test_compact_upload_gives_identical_results(cfg, n_docs, ops):
+    from peritext_b200.engine import BatchEngine, PipelinedEngine
+    batch = workload.generate(cfg, n_docs=n_docs, ops_per_doc=ops)
+    e = BatchEngine(0)
+    a = e.run(batch)
+    e.upload_compact(batch); e.merge(); b = e.download()
+    e.close()
+    assert a.results.tobytes() == b.results.tobytes() and a.text.tobytes() == b.text.tobytes()
+    for i in range(0, batch.n_logs, 7):
+        assert a.canonical(i) == b.canonical(i)
+    pipe = PipelinedEngine(0, chunks=3)
+    outs = pipe.run(batch, compact=True)
+    res = np.concatenate([o.results for o in outs])
+    assert res["digest"].tobytes() == a.results["digest"].tobytes() and (res["status"] == 0).all()
+    pipe.close()
