@@ -90,7 +90,7 @@ size_t arena_worst_bytes(uint64_t n, uint64_t m, uint64_t KS) {
         A(KW + 1, 4); A(KW + 1, I); for (int k = 0; k < 6; k++) A(m + 1, I);       // KBits KPre ByRank MRank IvA IvB IvVA IvVB
         A(m + 1, 1); A(m + 1, 4); A(m + 1, 4);                                     // MKind MAttr CompactC
         A(NWp + 1, 4); A(NWp + 1, I);                                              // BndBits SegPre
-        A(3 * (2 * S + 2), 4); A(S + 1, 4); A(S + 1, 4); A(S + 2, 4);              // Tree[3] SegFlags SegLink CDiff
+        A(2 * S + 2, 4); A(S + 1, 4); A(S + 1, 4); A(S + 2, 4);                    // Tree SegFlags SegLink CDiff
         A(n / 32 + 3, 4); A(Mc + 1, 4); A(Mc + 1, I); A(Mc + 1, I); A(Mc + 1, I);  // CHead CId CK CG0 CGn
         A(2 * Mc + 1, I); A(2 * Mc + 1, I);                                        // PcA PcB
         A(4 * Mc + 8, 4); A(4 * Mc + 9, 4); A(4 * Mc + 9, I); A(Mc + 1, I);        // HTab HCnt HOff CSlot
@@ -471,8 +471,10 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
         // typical shared-memory need (runs ~ n/6, segments ~ min(2m, n/2)); a wrong guess only costs a device-side deferral
         {
             const uint64_t I = (L.n_insdel < 32000 && L.n_mark < 32000) ? 2 : 4, n_ = L.n_insdel, m_ = L.n_mark;
+            // id table + bitmaps / run offsets (~1.4 B per record) + the larger of the run-tree temporaries (~5 B per record
+            // for typing-heavy logs) and the mark tables (per-op arrays + ~18 B per elementary segment)
             const uint64_t seg = std::min<uint64_t>(2 * m_ + 2, n_ / 2 + 2);
-            const uint64_t typical = KS * I + 6 * n_ + (m_ ? m_ * (6 * I + 9) + 32 * seg + 4096 : 0);
+            const uint64_t typical = KS * I + (14 * n_) / 10 + std::max<uint64_t>(5 * n_, m_ ? m_ * (6 * I + 13) + 18 * seg : 0) + 2048;
             while (bin < kNumBins - 1 && typical > kBins[bin].smem) bin++;
         }
         // short logs: one warp per log (16-bit keys and indices).  Footprint estimate: id table (compact form with >= 3

@@ -441,11 +441,13 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
         if (m) {
             const unsigned long long NWp_ = (N + 32) / 32 + 1, KW_ = (KS + 31) / 32;
             const unsigned long long Sb = (2ull * m + 2 < (unsigned long long)N + 2 ? 2ull * m + 2 : (unsigned long long)N + 2) + 1;
-            const unsigned long long Mcb = McBound, Hb = 4 * Mcb + 8, VWb = (nvis + 31) / 32, nsp = nvis < 2ull * m + 1 ? nvis : 2ull * m + 1;
+            // spans: at most one per visible element and per mark boundary; typically far fewer — guess half, a log that needs
+            // more fails its allocation in phase I and is deferred then (nothing irreversible has happened by that point)
+            const unsigned long long Mcb = McBound, Hb = 4 * Mcb + 8, VWb = (nvis + 31) / 32, nsp = (nvis < 2ull * m + 1 ? nvis : 2ull * m + 1) / 2 + 16;
             const unsigned long long Pm = base + 6 * al((m + 1) * I) + al(m + 1) + 2 * al((m + 1) * 4ull) + al((NWp_ + 1) * 4) + al((NWp_ + 1) * I);
             const unsigned long long pG2 = Pm + al((KW_ + 1) * 4) + al((KW_ + 1) * I);
             const unsigned long long Q = Pm + 2 * al((Sb + 1) * 4);
-            const unsigned long long pG3 = Q + al(3 * (2 * Sb + 2) * 4) + al((Sb + 2) * 4);
+            const unsigned long long pG3 = Q + al((2 * Sb + 2) * 4) + al((Sb + 2) * 4);
             const unsigned long long Rr = Q + al((nvis / 32 + 2) * 4ull) + al((Mcb + 1) * 4) + 3 * al((Mcb + 1) * I) + 2 * al((2 * Mcb + 1) * I);
             const unsigned long long pH = Rr + 2 * al((Hb + 1) * 4) + al((Hb + 1) * I) + al((Mcb + 1) * I);
             const unsigned long long pI = Rr + al((nvis + 1ull) * I) + al((VWb + 1) * 4) + al((VWb + 1) * I) + al((nsp + 1) * I) + 3 * al((nsp + 1) * 4);
@@ -767,51 +769,60 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
             uint32_t w = x >> 5, b = x & 31;
             return (uint32_t)SegPre[w] + __popc(BndBits[w] & (0xFFFFFFFFu >> (31 - b)));
         };
-        // G3: stabbing max per LWW type: three iterative segment trees over segment ids (range atomicMax, point query)
+        // G3: stabbing max per LWW type: an iterative segment tree over segment ids (range atomicMax, point query), ONE type at
+        // a time in the same buffer (three trees at once were the peak of the whole pipeline's shared-memory footprint and
+        // pushed 10K-record logs with ~1K marks into the one-CTA-per-SM bin)
         const uint32_t TS = 2 * S + 2;
         PT_ALLOC(SegFlags, uint32_t, S + 1);
         PT_ALLOC(SegLink, uint32_t, S + 1);
         const uint32_t mark4_sm = A.sm_used; const unsigned long long mark4_gm = A.gm_used;
-        PT_ALLOC(Tree, uint32_t, 3 * TS);      // [strong | em | link]   (temporaries of G3)
+        PT_ALLOC(Tree, uint32_t, TS);          // temporaries of G3
         PT_ALLOC(CDiff, int, S + 2);
-        fill<uint32_t, BLOCK>(Tree, 3 * TS, 0u);
+        fill<uint32_t, BLOCK>(SegFlags, S + 1, 0u);
+        fill<uint32_t, BLOCK>(SegLink, S + 1, PT_ATTR_NONE);
         fill<int, BLOCK>(CDiff, S + 2, 0);
-        __syncthreads();
-        for (uint32_t k = tid; k < m; k += BLOCK) {
-            const uint32_t a = IvA[k], b = IvB[k];
-            if (a >= b) continue;
-            const uint32_t t = ((uint32_t)MKind[k] >> 1) & 3u;
-            const uint32_t sa = segOf(a), sb2 = segOf(b);
-            if (t == PT_MARK_COMMENT) { atomicAdd(&CDiff[sa], 1); atomicAdd(&CDiff[sb2], -1); continue; }   // G4 difference array
-            uint32_t* tr = Tree + (t == PT_MARK_STRONG ? 0u : t == PT_MARK_EM ? TS : 2 * TS);
-            const uint32_t v = (uint32_t)MRank[k] + 1u;
-            for (uint32_t l = sa + S, r = sb2 + S; l < r; l >>= 1, r >>= 1) {
-                if (l & 1u) atomicMax(&tr[l++], v);
-                if (r & 1u) atomicMax(&tr[--r], v);
+#pragma unroll 1
+        for (uint32_t pass = 0; pass < 3; pass++) {
+            const uint32_t ptype = pass == 0 ? PT_MARK_STRONG : pass == 1 ? PT_MARK_EM : PT_MARK_LINK;
+            fill<uint32_t, BLOCK>(Tree, TS, 0u);
+            __syncthreads();
+            for (uint32_t k = tid; k < m; k += BLOCK) {
+                const uint32_t a = IvA[k], b = IvB[k];
+                if (a >= b) continue;
+                const uint32_t t = ((uint32_t)MKind[k] >> 1) & 3u;
+                if (t == PT_MARK_COMMENT) { if (pass == 0) { atomicAdd(&CDiff[segOf(a)], 1); atomicAdd(&CDiff[segOf(b)], -1); } continue; }   // G4 difference array
+                if (t != ptype) continue;
+                const uint32_t sa = segOf(a), sb2 = segOf(b);
+                const uint32_t v = (uint32_t)MRank[k] + 1u;
+                for (uint32_t l = sa + S, r = sb2 + S; l < r; l >>= 1, r >>= 1) {
+                    if (l & 1u) atomicMax(&Tree[l++], v);
+                    if (r & 1u) atomicMax(&Tree[--r], v);
+                }
             }
+            __syncthreads();
+            // LWW winner of this type per segment (peritext.ts:304-313): present iff the max-opId covering op is an addMark
+            for (uint32_t s2 = tid; s2 < S; s2 += BLOCK) {
+                uint32_t w = 0;
+                for (uint32_t p = s2 + S; p >= 1; p >>= 1) w = max(w, Tree[p]);
+                if (w) {
+                    const uint32_t kk = ByRank[w - 1];
+                    if (!(MKind[kk] & 1u)) {
+                        SegFlags[s2] |= pass == 0 ? PT_SPAN_STRONG : pass == 1 ? PT_SPAN_EM : PT_SPAN_LINK;
+                        if (pass == 2) SegLink[s2] = MAttr[kk];
+                    }
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // per segment: LWW winners (peritext.ts:304-313) and G4 `comment` key present iff >= 1 comment op covers it (quirk Q3)
+        // G4: `comment` key present iff >= 1 comment op covers the segment (quirk Q3): running sum of the difference array
         {
             int carry = 0;
             for (uint32_t base = 0; base < S; base += BLOCK) {
                 const uint32_t s2 = base + tid;
-                uint32_t flags = 0, link = PT_ATTR_NONE;
-                int v = 0;
-                if (s2 < S) {
-                    uint32_t w0 = 0, w1 = 0, w2 = 0;
-                    for (uint32_t p = s2 + S; p >= 1; p >>= 1) { w0 = max(w0, Tree[p]); w1 = max(w1, Tree[TS + p]); w2 = max(w2, Tree[2 * TS + p]); }
-                    if (w0 && !(MKind[ByRank[w0 - 1]] & 1u)) flags |= PT_SPAN_STRONG;
-                    if (w1 && !(MKind[ByRank[w1 - 1]] & 1u)) flags |= PT_SPAN_EM;
-                    if (w2) { const uint32_t kk = ByRank[w2 - 1]; if (!(MKind[kk] & 1u)) { flags |= PT_SPAN_LINK; link = MAttr[kk]; } }
-                    v = CDiff[s2];
-                }
+                const int v = s2 < S ? CDiff[s2] : 0;
                 uint32_t total;
                 const uint32_t ex = block_scan_excl<BLOCK>((uint32_t)v, c, total);   // two's complement sums are fine
-                if (s2 < S) {
-                    if (carry + (int)ex + v > 0) flags |= PT_SPAN_COMMENT;
-                    SegFlags[s2] = flags; SegLink[s2] = link;
-                }
+                if (s2 < S && carry + (int)ex + v > 0) SegFlags[s2] |= PT_SPAN_COMMENT;
                 carry += (int)total;
             }
         }
