@@ -15,6 +15,7 @@
 #include "merge_kernel.cuh"
 #include "warp_kernel.cuh"
 #include "patch_kernel.cuh"
+#include "team_kernel.cuh"
 
 namespace {
 
@@ -68,6 +69,9 @@ BinCfg kBins[kNumBins] = {
     {12288u, 512, 112u * 1024u, 2},
     {0xFFFFFFFFu, 1024, 226u * 1024u, 1},
 };
+constexpr int kTeamWarps = 8;                 // team kernel (team_kernel.cuh): 8 warps per log, 4 logs per SM
+constexpr uint32_t kTeamSmem = 55u * 1024u;
+bool g_team_bin = true;
 bool g_warp_bin = true, g_warp_force = false;   // force: skip the host-side footprint estimate (tests of the device-side deferral)
 
 inline size_t al16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -380,6 +384,7 @@ struct pt_batch {
     std::vector<uint32_t> h_order;
     uint32_t bin_first[kNumBins + 1] = {0};
     uint32_t warp_compact = 0;              // bin 0: the first warp_compact logs use the compact id table
+    uint32_t team_count = 0;                // bin 0: the last team_count logs run on the team kernel
     size_t bin_slab[kNumBins] = {0};
     size_t retry_slab = 0;
     // device
@@ -415,12 +420,13 @@ const BinCfg kDefaultBins[kNumBins] = {kBins[0], kBins[1], kBins[2], kBins[3], k
 void load_bins_from_env() {
     // re-read whenever the variables change (tests flip PT_WARP between uploads to cross-check the two kernels)
     static std::string last = "\x01";
-    const char* we = getenv("PT_WARP"); const char* be = getenv("PT_BINS"); const char* fe = getenv("PT_WARP_FORCE");
-    const std::string cur = std::string(we ? we : "") + "|" + (be ? be : "") + "|" + (fe ? fe : "");
+    const char* we = getenv("PT_WARP"); const char* be = getenv("PT_BINS"); const char* fe = getenv("PT_WARP_FORCE"); const char* te0 = getenv("PT_TEAM");
+    const std::string cur = std::string(we ? we : "") + "|" + (be ? be : "") + "|" + (fe ? fe : "") + "|" + (te0 ? te0 : "");
     if (cur == last) return;
     last = cur;
     for (int i = 0; i < kNumBins; i++) kBins[i] = kDefaultBins[i];
     g_warp_bin = true; g_warp_force = fe && atoi(fe) != 0;
+    { const char* te = getenv("PT_TEAM"); g_team_bin = !(te && atoi(te) == 0); }
     if (const char* w = getenv("PT_WARP")) {
         unsigned long a, wp, sl, ct;
         if (sscanf(w, "%lu:%lu:%lu:%lu", &a, &wp, &sl, &ct) == 4 && (wp == 2 || wp == 4 || wp == 6 || wp == 8 || wp == 12 || wp == 16)) {
@@ -428,7 +434,7 @@ void load_bins_from_env() {
             sl &= ~(unsigned long)15;
             if (sl * wp <= 227 * 1024) kBins[0] = BinCfg{(uint32_t)a, (int)wp * 32, (uint32_t)sl, (int)ct};
         }
-        else if (atoi(w) == 0) g_warp_bin = false;
+        else if (atoi(w) == 0) { g_warp_bin = false; g_team_bin = false; }      // PT_WARP=0: CTA-per-log kernels only
     }
     const char* e = getenv("PT_BINS");
     if (!e) return;
@@ -455,7 +461,8 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
     b->h_desc.assign(ops->logs, ops->logs + ops->n_logs);
     b->h_text_off.resize(b->n_logs); b->h_span_off.resize(b->n_logs);
     uint64_t to = 0, so = 0, ncomment_bound = 0;
-    uint32_t n_compact = 0;
+    uint32_t n_compact = 0, n_team = 0;
+    std::vector<uint8_t> is_team(ops->n_logs, 0);
     std::vector<uint32_t> bins[kNumBins];
     for (int k = 0; k < kNumBins; k++) b->bin_slab[k] = 0;
     for (uint32_t i = 0; i < b->n_logs; i++) {
@@ -488,6 +495,10 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
         if (bin == 0) {   // bin 0 is launched twice: compact id table (>= 3 actors) / direct id table
             const uint64_t R_ = L.n_actors ? L.n_actors : 1;
             if (R_ >= 3 && R_ <= 30 && L.n_insdel <= 2046) n_compact++;
+        } else if (g_team_bin && !(b->limits.flags & PT_FLAG_EMIT_SEQUENCE) && L.n_mark == 0 && KS < 0xFFFFull && L.n_insdel < 0xFFFFu &&
+                   (3ull * L.n_insdel) / 4 + 2 * KS + 2ull * L.n_insdel + 1024 <= kTeamSmem) {
+            // medium logs without mark ops: a team of 8 warps per log, 4 logs per SM (team_kernel.cuh); rides in bin 0's list
+            bin = 0; is_team[i] = 1; n_team++;
         }
         bins[bin].push_back(i);
         if (KS > 0x7FFFFFFFull) { g_last_error = "max_ctr * n_actors too large; re-rank counters densely on the host"; return PT_ERR_INVALID; }
@@ -499,14 +510,15 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
     for (int k = 0; k < kNumBins; k++) {
         b->bin_first[k] = (uint32_t)b->h_order.size();
         auto& v = bins[k];
-        auto is_compact = [&](uint32_t x) { const pt_log_desc& D = b->h_desc[x]; const uint32_t R_ = D.n_actors ? D.n_actors : 1; return R_ >= 3 && R_ <= 30 && D.n_insdel <= 2046; };
+        // bin 0's list: [warp kernel, compact id table | warp kernel, direct id table | team kernel]
+        auto cat = [&](uint32_t x) { if (is_team[x]) return 2; const pt_log_desc& D = b->h_desc[x]; const uint32_t R_ = D.n_actors ? D.n_actors : 1; return (R_ >= 3 && R_ <= 30 && D.n_insdel <= 2046) ? 0 : 1; };
         std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) {
-            if (k == 0) { const bool cx = is_compact(x), cy = is_compact(y); if (cx != cy) return cx; }   // compact-table logs first
+            if (k == 0) { const int cx = cat(x), cy = cat(y); if (cx != cy) return cx < cy; }
             return (uint64_t)b->h_desc[x].n_insdel + b->h_desc[x].n_mark > (uint64_t)b->h_desc[y].n_insdel + b->h_desc[y].n_mark; });
         b->h_order.insert(b->h_order.end(), v.begin(), v.end());
     }
     b->bin_first[kNumBins] = (uint32_t)b->h_order.size();
-    b->warp_compact = n_compact;
+    b->warp_compact = n_compact; b->team_count = n_team;
     return PT_OK;
 }
 
@@ -610,12 +622,30 @@ int launch_warp_range(pt_batch* b, ptk::BatchParams P, uint32_t first, uint32_t 
     b->launches++;
     return PT_OK;
 }
+int launch_team_range(pt_batch* b, ptk::BatchParams P, uint32_t first, uint32_t cnt) {
+    if (!cnt) return PT_OK;
+    const uint32_t grid = (uint32_t)std::min<size_t>(cnt, (size_t)b->num_sms * 4);
+    uint32_t* counters = (uint32_t*)((char*)b->d_counters.p + 128);
+    uint32_t* lists = (uint32_t*)b->d_retry.p;
+    P.order = (const uint32_t*)b->d_order.p + b->bin_first[0] + first; P.n_work = cnt; P.n_work_dev = nullptr;
+    P.work_counter = counters + 3 * kNumBins + 1;
+    P.slab_bytes = 0;
+    P.retry_list = lists + (size_t)3 * b->n_logs;        // a log that does not fit goes to the 512-thread CTA bin (and on from there)
+    P.retry_count = counters + 2 * kNumBins + 3;
+    P.smem_arena_bytes = kTeamSmem;
+    PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_team_kernel<kTeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTeamSmem));
+    ptk::merge_logs_team_kernel<kTeamWarps><<<grid, kTeamWarps * 32, kTeamSmem, b->stream>>>(P);
+    PT_CUDA(cudaGetLastError());
+    b->launches++;
+    return PT_OK;
+}
 template <int WARPS>
 int launch_warp_bin_t(pt_batch* b, const ptk::BatchParams& P) {
-    const uint32_t cnt = b->bin_first[1] - b->bin_first[0];
+    const uint32_t cnt = b->bin_first[1] - b->bin_first[0] - b->team_count;
     int rc = launch_warp_range<WARPS, true>(b, P, 0, b->warp_compact, 0);
     if (rc) return rc;
-    return launch_warp_range<WARPS, false>(b, P, b->warp_compact, cnt - b->warp_compact, 3 * kNumBins);
+    if ((rc = launch_warp_range<WARPS, false>(b, P, b->warp_compact, cnt - b->warp_compact, 3 * kNumBins))) return rc;
+    return launch_team_range(b, P, cnt, b->team_count);
 }
 int launch_bin(pt_batch* b, int k, const ptk::BatchParams& P, bool retry) {
     if (!retry && b->bin_first[k + 1] == b->bin_first[k]) return PT_OK;

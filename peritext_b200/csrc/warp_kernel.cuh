@@ -375,7 +375,13 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             const bool valid = pos < M;
             const uint32_t r = valid ? (uint32_t)ByG[pos] : 0u;
             const uint32_t q = valid ? (uint32_t)Prun[r] : (0x10000u + lane);
-            const uint32_t mask = __match_any_sync(kFull, q);
+            // MATCH.ANY costs a pass per distinct value; siblings inside one chunk are the exception, so probe first: every lane
+            // writes its lane id into a scratch slot of its parent (the enter half of Next, unused until the tour is built)
+            if (valid) Next[q] = (uint16_t)lane;
+            __syncwarp();
+            const bool clash = valid && Next[q] != lane;
+            uint32_t mask = 1u << lane;
+            if (__any_sync(kFull, clash)) mask = __match_any_sync(kFull, q);
             const uint32_t lower = mask & lt;
             const uint32_t src = lower ? (31u - __clz(lower)) : lane;
             const uint32_t rs = __shfl_sync(kFull, r, src);
