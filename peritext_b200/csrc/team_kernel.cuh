@@ -191,8 +191,9 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
     uint16_t* RKey = A.alloc<uint16_t>(M + 2);
     uint16_t* Last = RKey;
     uint16_t* ByG = A.alloc<uint16_t>(M + 1);
-    const uint32_t uBytes = max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)(((nSp + 1) * 4 + 15) & ~15u));
-    char* U = A.alloc<char>(uBytes);
+    const uint32_t uBytes = max(max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)(((nSp + 1) * 4 + 15) & ~15u)),
+                                (uint32_t)(((M + 32) * 2 + 15) & ~15u));
+    char* U = A.alloc<char>(uBytes);     // successively: key bitmap + prefix | per-warp run lists of the threading | splitter summaries
     if (!A.fits()) return 1;
     uint32_t* KBits = reinterpret_cast<uint32_t*>(U);
     uint16_t* KPre = reinterpret_cast<uint16_t*>(U + (((KW + 1) * 4 + 15) & ~15u));
@@ -240,24 +241,53 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
     }
     __syncthreads();
     for (uint32_t x = tid; x < M + 2; x += NT) Last[x] = (uint16_t)kNone16;      // RKey, KBits, KPre are dead from here
-    if (tid == 0) { Sub[SPEND] = SPEND; Sub2[SPEND] = SPEND; }
     __syncthreads();
-    if (warp == 0) {
-        // thread the runs in ASCENDING key order (one warp; the chunks depend on each other through Last[]): the previously
-        // threaded child of the same parent is the next sibling in descending-opId order (src/micromerge.ts:628-635)
-#pragma unroll 1
+    {
+        // thread the runs in ASCENDING key order: the previously threaded child of the same parent is the next sibling in
+        // descending-opId order (src/micromerge.ts:628-635), the last one threaded is the first child.  The chain only links runs
+        // of ONE parent, so the parents are dealt over the warps (parent mod TEAM): every warp first extracts its runs from the
+        // key-ordered list (two streaming passes, stable), then threads its own short list; no two warps touch the same parent.
+        uint16_t* Lst = reinterpret_cast<uint16_t*>(U);            // (the key bitmap is dead; the splitter summaries come later)
+        uint32_t mine = 0;
         for (uint32_t cb = 0; cb < M; cb += 32) {
             const uint32_t pos = cb + lane;
-            const bool valid = pos < M;
-            const uint32_t r = valid ? (uint32_t)ByG[pos] : 0u;
+            const bool ok = pos < M && ((uint32_t)Prun[ByG[pos]] % TEAM) == warp;
+            mine += __popc(__ballot_sync(kFull, ok));
+        }
+        if (lane == 0) c.wa[warp] = mine;
+        __syncthreads();
+        uint32_t off = 0;
+        for (uint32_t w2 = 0; w2 < warp; w2++) off += c.wa[w2];
+        __syncthreads();                                           // (the bitmap region may be overwritten from here)
+        uint32_t o = off;
+        for (uint32_t cb = 0; cb < M; cb += 32) {
+            const uint32_t pos = cb + lane;
+            const uint32_t r = pos < M ? (uint32_t)ByG[pos] : 0u;
+            const bool ok = pos < M && ((uint32_t)Prun[r] % TEAM) == warp;
+            const uint32_t bal = __ballot_sync(kFull, ok);
+            if (ok) Lst[o + __popc(bal & lt)] = (uint16_t)r;
+            o += __popc(bal);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t cb = 0; cb < mine; cb += 32) {
+            const uint32_t pos = cb + lane;
+            const bool valid = pos < mine;
+            const uint32_t r = valid ? (uint32_t)Lst[off + pos] : 0u;
             const uint32_t q = valid ? (uint32_t)Prun[r] : (0x10000u + lane);
             // MATCH.ANY costs a pass per distinct value; siblings inside one chunk are rare, so probe first: every lane writes its
             // lane id into a scratch slot of its parent (the enter half of Next, unused until the tour is built) and reads it back
             if (valid) Next[q] = (uint16_t)lane;
             __syncwarp();
-            const bool clash = valid && Next[q] != lane;
+            const bool lost = valid && Next[q] != lane;
             uint32_t mask = 1u << lane;
-            if (__any_sync(kFull, clash)) mask = __match_any_sync(kFull, q);
+            if (__any_sync(kFull, lost)) {                         // only the lanes of clashing parents enter MATCH.ANY
+                if (lost) Next[q] = (uint16_t)kNone16;
+                __syncwarp();
+                const bool grouped = valid && Next[q] == kNone16;
+                const uint32_t pm = __ballot_sync(kFull, grouped);
+                if (grouped) mask = __match_any_sync(pm, q);
+            }
             const uint32_t lower = mask & lt;
             const uint32_t src = lower ? (31u - __clz(lower)) : lane;
             const uint32_t rs = __shfl_sync(kFull, r, src);
@@ -272,6 +302,7 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
         }
     }
     __syncthreads();
+    if (tid == 0) { Sub[SPEND] = SPEND; Sub2[SPEND] = SPEND; }
     for (uint32_t r = tid; r <= M; r += NT) { const uint32_t f = Last[r]; Next[r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); }
     if (tid == 0) { Wt[M] = 0; Next[(M + 1) + M] = (uint16_t)END; Next[END] = (uint16_t)END; }
     __syncthreads();

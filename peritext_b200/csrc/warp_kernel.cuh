@@ -379,9 +379,15 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             // writes its lane id into a scratch slot of its parent (the enter half of Next, unused until the tour is built)
             if (valid) Next[q] = (uint16_t)lane;
             __syncwarp();
-            const bool clash = valid && Next[q] != lane;
+            const bool lost = valid && Next[q] != lane;
             uint32_t mask = 1u << lane;
-            if (__any_sync(kFull, clash)) mask = __match_any_sync(kFull, q);
+            if (__any_sync(kFull, lost)) {                         // only the lanes of clashing parents enter MATCH.ANY
+                if (lost) Next[q] = (uint16_t)kNone16;
+                __syncwarp();
+                const bool grouped = valid && Next[q] == kNone16;
+                const uint32_t pm = __ballot_sync(kFull, grouped);
+                if (grouped) mask = __match_any_sync(pm, q);
+            }
             const uint32_t lower = mask & lt;
             const uint32_t src = lower ? (31u - __clz(lower)) : lane;
             const uint32_t rs = __shfl_sync(kFull, r, src);
