@@ -385,6 +385,7 @@ struct pt_batch {
     uint32_t bin_first[kNumBins + 1] = {0};
     uint32_t warp_compact = 0;              // bin 0: the first warp_compact logs use the compact id table
     uint32_t team_count = 0;                // bin 0: the last team_count logs run on the team kernel
+    uint32_t n_spill = 0, slab_slots = 0;   // logs that can spill / slab slots allocated
     size_t bin_slab[kNumBins] = {0};
     size_t retry_slab = 0;
     // device
@@ -461,7 +462,7 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
     b->h_desc.assign(ops->logs, ops->logs + ops->n_logs);
     b->h_text_off.resize(b->n_logs); b->h_span_off.resize(b->n_logs);
     uint64_t to = 0, so = 0, ncomment_bound = 0;
-    uint32_t n_compact = 0, n_team = 0;
+    uint32_t n_compact = 0, n_team = 0, n_spill = 0;
     std::vector<uint8_t> is_team(ops->n_logs, 0);
     std::vector<uint32_t> bins[kNumBins];
     for (int k = 0; k < kNumBins; k++) b->bin_slab[k] = 0;
@@ -502,7 +503,10 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
         }
         bins[bin].push_back(i);
         if (KS > 0x7FFFFFFFull) { g_last_error = "max_ctr * n_actors too large; re-rank counters densely on the host"; return PT_ERR_INVALID; }
-        b->bin_slab[bin] = std::max(b->bin_slab[bin], arena_worst_bytes(L.n_insdel, L.n_mark, KS));
+        {   // only a log whose worst-case working set exceeds the largest shared-memory budget can ever spill to the global slab
+            const size_t worst = arena_worst_bytes(L.n_insdel, L.n_mark, KS);
+            if (worst > kBins[kNumBins - 1].smem) { b->bin_slab[kNumBins - 1] = std::max(b->bin_slab[kNumBins - 1], worst); n_spill++; }
+        }
     }
     b->n_text = to; b->n_span = so;
     b->pool_cap = b->limits.comment_pool_entries ? b->limits.comment_pool_entries : 64ull * ncomment_bound + 1024;
@@ -518,7 +522,7 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
         b->h_order.insert(b->h_order.end(), v.begin(), v.end());
     }
     b->bin_first[kNumBins] = (uint32_t)b->h_order.size();
-    b->warp_compact = n_compact; b->team_count = n_team;
+    b->warp_compact = n_compact; b->team_count = n_team; b->n_spill = n_spill;
     return PT_OK;
 }
 
@@ -552,9 +556,11 @@ int alloc_and_upload_plan(pt_batch* b) {
         }
         b->patch_smem = (uint32_t)((need_max + 1023) & ~1023ull);
     }
-    size_t slab_total = 0, slab_max = 0;
-    for (int k = 0; k < kNumBins; k++) slab_max = std::max(slab_max, b->bin_slab[k]);
-    slab_total = (size_t)b->num_sms * kBins[kNumBins - 1].ctas_per_sm * slab_max;   // only the last bin can spill
+    // spill slab: one slot per CTA that can ever spill = min(logs that can spill, CTAs of the last bin); a batch with one huge
+    // log no longer multiplies its worst case by the whole grid
+    const size_t slab_max = b->bin_slab[kNumBins - 1];
+    b->slab_slots = (uint32_t)std::min<size_t>(b->n_spill, (size_t)b->num_sms * kBins[kNumBins - 1].ctas_per_sm);
+    const size_t slab_total = (size_t)b->slab_slots * slab_max;
     b->retry_slab = slab_max;
     if ((rc = b->d_slab.reserve(std::max<size_t>(slab_total, 16)))) return rc;
     // stage the small host-derived arrays through pinned memory
@@ -592,6 +598,7 @@ int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P, bool retry) {
     }
     const bool last = k == kNumBins - 1;
     P.slab_bytes = last ? b->retry_slab : 0;
+    if (retry) P.slab_counter += 1;      // the two launches of the last bin run one after the other: each counts its slots from zero
     P.retry_list = last ? nullptr : lists + (size_t)(k + 1) * b->n_logs;
     P.retry_count = last ? nullptr : counters + 2 * kNumBins + (k + 1);
     P.smem_arena_bytes = cfg.smem;
@@ -920,6 +927,7 @@ static int enqueue_merge(pt_batch* b) {
     P.text = (uint32_t*)b->d_text.p; P.spans = (pt_span*)b->d_spans.p;
     P.comment_pool = (uint32_t*)b->d_pool.p; P.comment_used = (unsigned long long*)((char*)b->d_counters.p + 64); P.comment_cap = b->pool_cap;
     P.slab = (char*)b->d_slab.p;
+    P.slab_counter = (uint32_t*)((char*)b->d_counters.p + 96); P.slab_slots = b->slab_slots;
     P.seq = (b->limits.flags & PT_FLAG_EMIT_SEQUENCE) ? (uint32_t*)b->d_seq.p : nullptr;
     P.stats = (unsigned long long*)b->d_counters.p;
     P.admit = nullptr;

@@ -44,8 +44,10 @@ struct BatchParams {
     uint32_t* comment_pool;
     unsigned long long* comment_used;
     unsigned long long comment_cap;
-    char* slab;                           // spill: slab_bytes per CTA
+    char* slab;                           // spill: slab_bytes per SPILLING CTA (a CTA takes a slot the first time it spills)
     unsigned long long slab_bytes;
+    uint32_t* slab_counter;               // next free slab slot
+    uint32_t slab_slots;                  // slots allocated: min(logs that can spill, grid)
     uint32_t smem_arena_bytes;            // dynamic shared memory given to the arena
     unsigned long long* stats;            // [0] logs finished on the shared-only path, [1] on the spill path, [2] deferred
     uint32_t* retry_list;                 // non-null: logs that do not fit this bin's shared memory are deferred here
@@ -99,6 +101,7 @@ struct BlockCtx {
     uint32_t work, work_next;
     uint32_t misc[4];
     uint32_t dup_cnt;                   // occupied id-table entries (must equal the number of inserts)
+    uint32_t slab_slot;                 // this CTA's slot of the global spill slab (0xFFFFFFFF: none taken yet)
     unsigned long long dig0, dig1;
     unsigned long long pool_base;
 };
@@ -247,7 +250,13 @@ __device__ int merge_one_log(const BatchParams& P, uint32_t li, BlockCtx<BLOCK>&
 
     Arena<SH> A;
     A.sm_cap = P.smem_arena_bytes; A.sm_used = 0;
-    A.gm = P.slab + (unsigned long long)blockIdx.x * P.slab_bytes; A.gm_cap = P.slab_bytes; A.gm_used = 0; A.overflow = false;
+    A.gm = P.slab; A.gm_cap = 0; A.gm_used = 0; A.overflow = false;
+    if (!SH) {
+        // the global slab has one slot per CTA that ever spills (only logs whose worst case exceeds the shared-memory budget can)
+        if (tid == 0 && c.slab_slot == 0xFFFFFFFFu) c.slab_slot = atomicAdd(P.slab_counter, 1u);
+        __syncthreads();
+        if (c.slab_slot < P.slab_slots) { A.gm = P.slab + (unsigned long long)c.slab_slot * P.slab_bytes; A.gm_cap = P.slab_bytes; }
+    }
 
     if (tid == 0) { c.status = 0; c.misc[0] = 0; c.misc[2] = 0; c.misc[3] = 0; c.dup_cnt = 0; c.dig0 = 0; c.dig1 = 0; c.pool_base = 0; }
 
@@ -1060,7 +1069,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : BLOCK == 256 ? 3 : 
     __shared__ BlockCtx<BLOCK> ctx;
     const uint32_t n_work = P.n_work_dev ? *P.n_work_dev : P.n_work;
     uint32_t tma_parity = 0;                // bit b: parity to wait for on staging barrier b (uniform across the CTA)
-    if (threadIdx.x == 0) { ctx.work_next = atomicAdd(P.work_counter, 1u); mbar_init(&ctx.tma_bar[0], 1); mbar_init(&ctx.tma_bar[1], 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) { ctx.work_next = atomicAdd(P.work_counter, 1u); ctx.slab_slot = 0xFFFFFFFFu; mbar_init(&ctx.tma_bar[0], 1); mbar_init(&ctx.tma_bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     for (;;) {
         const uint32_t w = ctx.work_next;
