@@ -404,6 +404,8 @@ struct pt_batch {
     // pinned host
     HostBuf h_stage, h_results, h_text, h_spans, h_pool, h_misc, h_seq, h_ctoff, h_csoff;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t side = nullptr, launch_stream = nullptr;   // side: the CTA-per-log bins' own launches run beside the warp / team kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t launches = 0;
     cudaGraphExec_t graph_exec = nullptr;   // the merge sequence of the current batch, captured once
     bool graph_ok = false, graph_tried = false;
@@ -603,7 +605,7 @@ int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P, bool retry) {
     P.retry_count = last ? nullptr : counters + 2 * kNumBins + (k + 1);
     P.smem_arena_bytes = cfg.smem;
     PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_kernel<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    ptk::merge_logs_kernel<BLOCK><<<grid, BLOCK, cfg.smem, b->stream>>>(P);
+    ptk::merge_logs_kernel<BLOCK><<<grid, BLOCK, cfg.smem, b->launch_stream>>>(P);
     PT_CUDA(cudaGetLastError());
     b->launches++;
     return PT_OK;
@@ -624,7 +626,7 @@ int launch_warp_range(pt_batch* b, ptk::BatchParams P, uint32_t first, uint32_t 
     P.smem_arena_bytes = cfg.smem;                       // per warp
     const int smem = (int)(cfg.smem * WARPS);
     PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_warp_kernel<WARPS, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ptk::merge_logs_warp_kernel<WARPS, COMPACT><<<grid, WARPS * 32, smem, b->stream>>>(P);
+    ptk::merge_logs_warp_kernel<WARPS, COMPACT><<<grid, WARPS * 32, smem, b->launch_stream>>>(P);
     PT_CUDA(cudaGetLastError());
     b->launches++;
     return PT_OK;
@@ -641,7 +643,7 @@ int launch_team_range(pt_batch* b, ptk::BatchParams P, uint32_t first, uint32_t 
     P.retry_count = counters + 2 * kNumBins + 3;
     P.smem_arena_bytes = kTeamSmem;
     PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_team_kernel<kTeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTeamSmem));
-    ptk::merge_logs_team_kernel<kTeamWarps><<<grid, kTeamWarps * 32, kTeamSmem, b->stream>>>(P);
+    ptk::merge_logs_team_kernel<kTeamWarps><<<grid, kTeamWarps * 32, kTeamSmem, b->launch_stream>>>(P);
     PT_CUDA(cudaGetLastError());
     b->launches++;
     return PT_OK;
@@ -698,6 +700,11 @@ int pt_batch_create(int device, const pt_limits* limits, void* cuda_stream, pt_b
     if (limits) b->limits = *limits;
     if (b->limits.flags & PT_FLAG_EMIT_PATCHES) b->limits.flags |= PT_FLAG_EMIT_SEQUENCE;
     if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) { delete b; g_last_error = "cudaEventCreate failed"; return PT_ERR_CUDA; }
+    if (b->stream != nullptr) {          // fork / join needs a real stream (not the legacy default stream)
+        if (cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); b->side = nullptr; }
+    }
+    b->launch_stream = b->stream;
     *out = b;
     return PT_OK;
 }
@@ -950,11 +957,30 @@ static int enqueue_merge(pt_batch* b) {
     int rc;
     // ascending bins; a log whose working set does not fit bin k's shared memory is deferred (on the device) to bin k+1;
     // only the last bin can spill to the global slab
-    bool lower = false;
-    for (int k = 0; k < kNumBins; k++) {
-        if ((rc = launch_bin(b, k, P, false))) return rc;
-        if (k > 0 && lower && (rc = launch_bin(b, k, P, true))) return rc;
-        lower = lower || b->bin_first[k + 1] > b->bin_first[k];
+    // The CTA-per-log bins' own lists do not depend on the warp / team kernels: when both exist they are launched on a side
+    // stream (fork / join, also inside the captured graph) and fill the SMs the warp kernel's tail leaves idle.  The deferral
+    // launches come after the join, in ascending bin order.
+    const bool have0 = b->bin_first[1] > b->bin_first[0], haveBlocks = b->bin_first[kNumBins] > b->bin_first[1];
+    const bool fork = have0 && haveBlocks && b->side != nullptr;
+    if (fork) {
+        PT_CUDA(cudaEventRecord(b->ev_fork, b->stream));
+        PT_CUDA(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
+        b->launch_stream = b->side;
+    }
+    if (fork) {
+        for (int k = 1; k < kNumBins; k++) if ((rc = launch_bin(b, k, P, false))) { b->launch_stream = b->stream; return rc; }
+        PT_CUDA(cudaEventRecord(b->ev_join, b->side));
+        b->launch_stream = b->stream;
+        if ((rc = launch_bin(b, 0, P, false))) return rc;
+        PT_CUDA(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
+        for (int k = 1; k < kNumBins; k++) if ((rc = launch_bin(b, k, P, true))) return rc;
+    } else {
+        bool lower = false;
+        for (int k = 0; k < kNumBins; k++) {
+            if ((rc = launch_bin(b, k, P, false))) return rc;
+            if (k > 0 && lower && (rc = launch_bin(b, k, P, true))) return rc;
+            lower = lower || b->bin_first[k + 1] > b->bin_first[k];
+        }
     }
     if ((b->limits.flags & PT_FLAG_EMIT_PATCHES) && b->n_logs) {
         ptk::PatchParams Q{};
@@ -1224,6 +1250,9 @@ void pt_batch_destroy(pt_batch* b) {
                       &b->d_cdesc, &b->d_changes, &b->d_deps, &b->d_admit, &b->d_patch_recs, &b->d_patch_items, &b->d_patch_status}) d->release();
     for (HostBuf* h : {&b->h_patch_recs, &b->h_patch_items, &b->h_patch_status, &b->h_patch_misc}) h->release();
     for (HostBuf* h : {&b->h_stage, &b->h_results, &b->h_text, &b->h_spans, &b->h_pool, &b->h_misc, &b->h_seq, &b->h_ctoff, &b->h_csoff}) h->release();
+    if (b->side) cudaStreamDestroy(b->side);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
