@@ -131,3 +131,16 @@ def test_nested_and_identical_ranges_without_comment_race(engine):
     check(engine, docs, logs)
     spans = [d.getTextWithFormatting() for d in docs]
     assert spans[0] == spans[1] == spans[2]       # no same-id race: the replicas converge
+
+
+def test_many_actors_share_counters_compact_table_overflows(engine):
+    # 12 replicas insert concurrently at one position, round after round: every counter value is used by 12 inserts, far more
+    # than the warp kernel's overflow table for its compact id table holds -> the log is deferred on the device; same results
+    docs, logs, q, do = session(12, "xy")
+    for rnd in range(6):
+        for a in range(12):
+            do(a, [dict(action="insert", index=1, values=list("%x%d" % (a, rnd)))])
+        sync_all(docs, logs, q)
+    check(engine, docs, logs)
+    spans = [d.getTextWithFormatting() for d in docs]
+    assert all(s == spans[0] for s in spans)
