@@ -63,7 +63,7 @@ struct BinCfg { uint32_t max_recs; int block; uint32_t smem; int ctas_per_sm; };
 // Bin 0 is the WARP-PER-LOG kernel (warp_kernel.cuh): block = warps per CTA * 32, smem = bytes PER WARP; a log it cannot
 // finish is deferred on the device to bin 1.  Bins 1..4 are the CTA-per-log kernel (merge_kernel.cuh).
 BinCfg kBins[kNumBins] = {
-    {2048u, 8 * 32, 6656u, 4},
+    {2048u, 8 * 32, 7136u, 4},
     {1536u, 128, 31u * 1024u, 7},
     {4096u, 256, 74u * 1024u, 3},
     {12288u, 512, 112u * 1024u, 2},
@@ -383,7 +383,8 @@ struct pt_batch {
     std::vector<uint64_t> h_text_off, h_span_off;
     std::vector<uint32_t> h_order;
     uint32_t bin_first[kNumBins + 1] = {0};
-    uint32_t warp_compact = 0;              // bin 0: the first warp_compact logs use the compact id table
+    uint32_t warp_packed = 0;               // bin 0: the first warp_packed logs use the packed3 id table (3 actors, <= 1022 records)
+    uint32_t warp_compact = 0;              // bin 0: the next warp_compact logs use the compact id table
     uint32_t team_count = 0;                // bin 0: the last team_count logs run on the team kernel
     uint32_t n_spill = 0, slab_slots = 0;   // logs that can spill / slab slots allocated
     size_t bin_slab[kNumBins] = {0};
@@ -464,7 +465,7 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
     b->h_desc.assign(ops->logs, ops->logs + ops->n_logs);
     b->h_text_off.resize(b->n_logs); b->h_span_off.resize(b->n_logs);
     uint64_t to = 0, so = 0, ncomment_bound = 0;
-    uint32_t n_compact = 0, n_team = 0, n_spill = 0;
+    uint32_t n_packed = 0, n_compact = 0, n_team = 0, n_spill = 0;
     std::vector<uint8_t> is_team(ops->n_logs, 0);
     std::vector<uint32_t> bins[kNumBins];
     for (int k = 0; k < kNumBins; k++) b->bin_slab[k] = 0;
@@ -492,12 +493,16 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
         // a device-side deferral
         if (g_warp_bin && !(b->limits.flags & PT_FLAG_EMIT_SEQUENCE) && recs <= kBins[0].max_recs && KS < 0xFFFFull) {
             const uint64_t R_ = L.n_actors ? L.n_actors : 1, n_ = L.n_insdel;
-            const uint64_t idbytes = (R_ >= 3 && R_ <= 30 && n_ <= 2046) ? 2ull * L.max_ctr + 512 : 2 * KS;
-            if (g_warp_force || idbytes + n_ / 2 + 16 * n_ / 3 + 1024 <= kBins[0].smem) bin = 0;
+            const bool packed3 = R_ == 3 && n_ <= 1022;
+            const uint64_t idbytes = packed3 ? 4ull * L.max_ctr : (R_ >= 3 && R_ <= 30 && n_ <= 2046) ? 2ull * L.max_ctr + 512 : 2 * KS;
+            // packed3 (three concurrent replicas): per-word state 16 B per 32 records, ~14 B per run for ~ n/4 runs, key bitmap + prefix
+            const uint64_t rest = packed3 ? n_ / 2 + 32 + 14 * (n_ / 4) + (KS / 32 + 2) * 6 + 512 : n_ / 2 + 16 * n_ / 3 + 1024;
+            if (g_warp_force || idbytes + rest <= kBins[0].smem) bin = 0;
         }
-        if (bin == 0) {   // bin 0 is launched twice: compact id table (>= 3 actors) / direct id table
+        if (bin == 0) {   // bin 0's warp launches: packed3 id table (3 actors) / compact (>= 3 actors) / direct
             const uint64_t R_ = L.n_actors ? L.n_actors : 1;
-            if (R_ >= 3 && R_ <= 30 && L.n_insdel <= 2046) n_compact++;
+            if (R_ == 3 && L.n_insdel <= 1022) n_packed++;
+            else if (R_ >= 3 && R_ <= 30 && L.n_insdel <= 2046) n_compact++;
         } else if (g_team_bin && !(b->limits.flags & PT_FLAG_EMIT_SEQUENCE) && L.n_mark == 0 && KS < 0xFFFFull && L.n_insdel < 0xFFFFu &&
                    (3ull * L.n_insdel) / 4 + 2 * KS + 2ull * L.n_insdel + 1024 <= kTeamSmem) {
             // medium logs without mark ops: a team of 8 warps per log, 4 logs per SM (team_kernel.cuh); rides in bin 0's list
@@ -516,15 +521,16 @@ int plan_batch(pt_batch* b, const pt_packed_ops* ops) {
     for (int k = 0; k < kNumBins; k++) {
         b->bin_first[k] = (uint32_t)b->h_order.size();
         auto& v = bins[k];
-        // bin 0's list: [warp kernel, compact id table | warp kernel, direct id table | team kernel]
-        auto cat = [&](uint32_t x) { if (is_team[x]) return 2; const pt_log_desc& D = b->h_desc[x]; const uint32_t R_ = D.n_actors ? D.n_actors : 1; return (R_ >= 3 && R_ <= 30 && D.n_insdel <= 2046) ? 0 : 1; };
+        // bin 0's list: [warp kernel, packed3 id table | compact id table | direct id table | team kernel]
+        auto cat = [&](uint32_t x) { if (is_team[x]) return 3; const pt_log_desc& D = b->h_desc[x]; const uint32_t R_ = D.n_actors ? D.n_actors : 1;
+                                     return (R_ == 3 && D.n_insdel <= 1022) ? 0 : (R_ >= 3 && R_ <= 30 && D.n_insdel <= 2046) ? 1 : 2; };
         std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) {
             if (k == 0) { const int cx = cat(x), cy = cat(y); if (cx != cy) return cx < cy; }
             return (uint64_t)b->h_desc[x].n_insdel + b->h_desc[x].n_mark > (uint64_t)b->h_desc[y].n_insdel + b->h_desc[y].n_mark; });
         b->h_order.insert(b->h_order.end(), v.begin(), v.end());
     }
     b->bin_first[kNumBins] = (uint32_t)b->h_order.size();
-    b->warp_compact = n_compact; b->team_count = n_team; b->n_spill = n_spill;
+    b->warp_packed = n_packed; b->warp_compact = n_compact; b->team_count = n_team; b->n_spill = n_spill;
     return PT_OK;
 }
 
@@ -610,7 +616,7 @@ int launch_bin_t(pt_batch* b, int k, ptk::BatchParams P, bool retry) {
     b->launches++;
     return PT_OK;
 }
-template <int WARPS, bool COMPACT>
+template <int WARPS, int IDM>
 int launch_warp_range(pt_batch* b, ptk::BatchParams P, uint32_t first, uint32_t cnt, uint32_t counter_slot) {
     if (!cnt) return PT_OK;
     const BinCfg& cfg = kBins[0];
@@ -625,8 +631,8 @@ int launch_warp_range(pt_batch* b, ptk::BatchParams P, uint32_t first, uint32_t 
     P.retry_count = counters + 2 * kNumBins + 1;
     P.smem_arena_bytes = cfg.smem;                       // per warp
     const int smem = (int)(cfg.smem * WARPS);
-    PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_warp_kernel<WARPS, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ptk::merge_logs_warp_kernel<WARPS, COMPACT><<<grid, WARPS * 32, smem, b->launch_stream>>>(P);
+    PT_CUDA(cudaFuncSetAttribute(ptk::merge_logs_warp_kernel<WARPS, IDM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ptk::merge_logs_warp_kernel<WARPS, IDM><<<grid, WARPS * 32, smem, b->launch_stream>>>(P);
     PT_CUDA(cudaGetLastError());
     b->launches++;
     return PT_OK;
@@ -651,9 +657,11 @@ int launch_team_range(pt_batch* b, ptk::BatchParams P, uint32_t first, uint32_t 
 template <int WARPS>
 int launch_warp_bin_t(pt_batch* b, const ptk::BatchParams& P) {
     const uint32_t cnt = b->bin_first[1] - b->bin_first[0] - b->team_count;
-    int rc = launch_warp_range<WARPS, true>(b, P, 0, b->warp_compact, 0);
+    const uint32_t np = b->warp_packed, nc = b->warp_compact;
+    int rc = launch_warp_range<WARPS, ptk::kIdPacked3>(b, P, 0, np, 3 * kNumBins + 2);
     if (rc) return rc;
-    if ((rc = launch_warp_range<WARPS, false>(b, P, b->warp_compact, cnt - b->warp_compact, 3 * kNumBins))) return rc;
+    if ((rc = launch_warp_range<WARPS, ptk::kIdCompact>(b, P, np, nc, 0))) return rc;
+    if ((rc = launch_warp_range<WARPS, ptk::kIdDirect>(b, P, np + nc, cnt - np - nc, 3 * kNumBins))) return rc;
     return launch_team_range(b, P, cnt, b->team_count);
 }
 int launch_bin(pt_batch* b, int k, const ptk::BatchParams& P, bool retry) {

@@ -77,8 +77,11 @@ __device__ __forceinline__ void wfill(T* p, uint32_t count, T v, uint32_t lane) 
     for (uint32_t i = lane; i < nvec; i += 32) d[i] = q;
 }
 
-// returns 0: done (result header written), 1: defer to the block kernel.  COMPACT selects the id-table form (below).
-template <bool COMPACT>
+// id-table forms of the warp kernel (one kernel instantiation each; the host sorts the logs into the launches)
+constexpr int kIdDirect = 0, kIdCompact = 1, kIdPacked3 = 2;
+
+// returns 0: done (result header written), 1: defer to the block kernel.  IDM selects the id-table form (below).
+template <int IDM>
 __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const uint32_t li, const uint32_t slice_base, const uint32_t slice_bytes, const uint32_t li_next, PhaseSync ps) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt = (1u << lane) - 1u;
@@ -116,8 +119,12 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
     //          bounds the number of resident warps.  T[ctr-1] = actor:5 | index:11 of ONE insert with that counter; the few
     //          inserts that share a counter with an earlier one (concurrent edits) go to a small open-addressing overflow
     //          table OV (key:16 | index:16, linear probing).  More than kOvMax of those: the log is deferred.
-    constexpr bool compact = COMPACT;
+    // packed3: exactly 3 actors and <= 1022 records (c4's shape: three concurrent replicas): one 32-bit word per COUNTER holds
+    //          the three actors' record indices + 1 in 10-bit fields.  An insert is ONE atomicOr (the old value tells a
+    //          duplicate opId), a lookup one LDS + shift + mask; no overflow table, nothing to probe.
+    constexpr bool compact = IDM == kIdCompact, packed = IDM == kIdPacked3;
     if (compact && !(R >= 3u && R <= 30u && n <= 2046u)) { ps.leave(); return 1; }     // (the host only sends such logs to this launch)
+    if (packed && !(R == 3u && n <= 1022u)) { ps.leave(); return 1; }
     constexpr uint32_t kOvSlots = 128, kOvMax = 96, kOvEmpty = 0xFFFFFFFFu;
     const uint32_t NWr = (n + 31) / 32 + 1;                    // bit words over record indices (+1 zero pad word)
     // layout: the arrays at FIXED offsets first (their addresses are one add away from the slice base)
@@ -125,11 +132,13 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
     // per 32-record word: x = insert bits, y = chain-link bits (after C: run-head bits), z = visible bits (after C),
     // w = run heads before the word | visible elements before the word << 16 (after C)
     uint4* WI = A.alloc<uint4>(NWr);
-    uint16_t* T = A.alloc<uint16_t>(compact ? C : KS);
+    uint16_t* T = A.alloc<uint16_t>(packed ? 2u * C : compact ? C : KS);
+    uint32_t* T32 = reinterpret_cast<uint32_t*>(T);              // packed3 view
     const uint32_t markC = A.used;
     uint2* OD = A.alloc<uint2>(NWr);                           // x = element has a child that is not its log successor, y = tombstone (dead after C)
     if (!A.fits()) { ps.leave(); return 1; }
-    wfill<uint16_t>(T, compact ? C : KS, (uint16_t)kNone16, lane);
+    if (packed) wfill<uint32_t>(T32, C, 0u, lane);
+    else wfill<uint16_t>(T, compact ? C : KS, (uint16_t)kNone16, lane);
     if (compact) wfill<uint32_t>(OV, kOvSlots, kOvEmpty, lane);
     wfill<uint32_t>(reinterpret_cast<uint32_t*>(OD), 2 * NWr, 0u, lane);
     if (lane == 0) WI[NWr - 1] = make_uint4(0, 0, 0, 0);
@@ -137,6 +146,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
     auto ovHash = [&](uint32_t key) -> uint32_t { return ((key * 40503u) >> 7) & (kOvSlots - 1u); };
     // index of the insert record with opId (ctr, actor), kNone16 if there is none; the id must be in range (!badId)
     auto lookup = [&](uint32_t ctr, uint32_t actor) -> uint32_t {
+        if (packed) { const uint32_t f = (T32[ctr - 1u] >> (10u * actor)) & 1023u; return f ? f - 1u : kNone16; }
         if (!compact) return T[keyOf(ctr, actor)];
         const uint32_t e = T[ctr - 1u];
         if (e == kNone16) return kNone16;                      // no insert with this counter at all
@@ -158,22 +168,21 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         uint32_t carryK = 0xFFFFFFFFu;                         // key of the last record of the previous trip if it is an insert
         // records past the end are loaded from a clamped index and ignored (every use is guarded by i < n)
         const uint32_t nm1 = n ? n - 1u : 0u;
-        uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
-        if (n) { ra = ld_rec(ins + min(lane, nm1)); rb = ld_rec(ins + min(32u + lane, nm1)); }
-        // an L2 prefetch stream runs kPfTrips trips (512 B each) ahead of the register loads: DRAM latency under load is
-        // longer than two trips
-        constexpr uint32_t kPfTrips = 8;
+        uint4 ra = make_uint4(0, 0, 0, 0);
+        if (n) ra = ld_rec(ins + min(lane, nm1));
+        // an L2 prefetch stream runs >= 10 trips (512 B each) ahead of the register loads: DRAM latency under load is longer than
+        // two trips.  Every 8th trip all 32 lanes fetch the 32 lines of 8 later trips (one uniform branch per trip otherwise).
         const char* insb = reinterpret_cast<const char*>(ins);
         const uint32_t insBytes = n * 16u;
         if (lane * 128u + 1024u < insBytes) prefetch_l2(insb + 1024u + lane * 128u);          // trips 2 .. 9
-        const char* pfp = insb + (kPfTrips + 2u) * 512u + lane * 128u;                      // lanes 0..3: the 4 lines of a trip
-        uint32_t pfo = (kPfTrips + 2u) * 512u + lane * 128u + (lane < 4u ? 0u : 0x40000000u);
-#pragma unroll 1
+#pragma unroll 2
         for (uint32_t base = 0; base < n; base += 32) {
             const uint32_t i = base + lane;
-            if (pfo < insBytes) prefetch_l2(pfp);
-            pfp += 512; pfo += 512;
-            const uint4 rc = ld_rec(ins + min(i + 64u, nm1));
+            if ((base & 255u) == 0u) {                                                       // trips t+10 .. t+17
+                const uint32_t po = (base + 320u) * 16u + lane * 128u;
+                if (po < insBytes) prefetch_l2(insb + po);
+            }
+            const uint4 rc = ld_rec(ins + min(i + 32u, nm1));           // one trip ahead (the lines are in L2 by now); unrolled by 2: no moves
             const uint4 r = ra;
             const uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16, kind = r.w >> 30;
             bool isIns = false, valid = false, toOv = false, wrote = false;
@@ -185,7 +194,10 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
                     valid = true; key = keyOf(ctr, actor);
                     if (kind == PT_KIND_INSERT) {
                         isIns = true;
-                        if (!compact) {
+                        if (packed) {
+                            const uint32_t sh = 10u * actor;
+                            if ((atomicOr(&T32[ctr - 1u], (i + 1u) << sh) >> sh) & 1023u) fail(PT_LOG_BAD_OPID);   // two inserts with one opId
+                        } else if (!compact) {
                             if (T[key] != kNone16) fail(PT_LOG_BAD_OPID);      // two inserts with one opId (earlier trip)
                             T[key] = (uint16_t)i;
                         } else {
@@ -209,9 +221,9 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             const uint32_t insW = __ballot_sync(kFull, isIns), candW = __ballot_sync(kFull, cand);
             if (lane == 0) *reinterpret_cast<uint2*>(&WI[base >> 5]) = make_uint2(insW, candW);
             __syncwarp();                                          // the trip's ids are in T
-            if (!compact) {
+            if (IDM == kIdDirect) {
                 if (isIns && T[key] != (uint16_t)i) fail(PT_LOG_BAD_OPID);   // two inserts with one opId (same trip)
-            } else {
+            } else if (compact) {
                 if (wrote) {                                       // same counter twice in one trip: one lane owns the slot
                     const uint32_t e2 = T[ctr - 1u];
                     if (e2 != mine) { if ((e2 >> 11) == actor) fail(PT_LOG_BAD_OPID); else toOv = true; }
@@ -239,12 +251,12 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
                     else atomicOr(reinterpret_cast<uint32_t*>(&OD[j >> 5]) + (isIns ? 0u : 1u), 1u << (j & 31));   // deletes: OR, idempotent (micromerge.ts:689)
                 }
             }
-            ra = rb; rb = rc;
+            ra = rc;
         }
     }
     __syncwarp();
     ps.pass();                                                     // (2) end of the record pass
-    if (nOv > kOvMax) { ps.leave(); return 1; }                                    // too many concurrent-counter inserts for the compact table
+    if (compact && nOv > kOvMax) { ps.leave(); return 1; }                                    // too many concurrent-counter inserts for the compact table
     st = __reduce_max_sync(kFull, st);
     if (st) { bail(st); ps.leave(); return 0; }
 
@@ -511,18 +523,16 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         const uint4* mq = reinterpret_cast<const uint4*>(mk);
         const uint32_t mm1 = m - 1u;                               // m > 0 here; past-the-end lanes load a clamped record, unused
         uint4 a0 = __ldg(mq + 2 * min(lane, mm1)), a1 = __ldg(mq + 2 * min(lane, mm1) + 1);
-        uint4 c0 = __ldg(mq + 2 * min(lane + 32u, mm1)), c1 = __ldg(mq + 2 * min(lane + 32u, mm1) + 1);
         const uint32_t mkBytes = m * 32u;
-        const char* mpf = reinterpret_cast<const char*>(mk) + 6u * 1024u + lane * 128u;      // lanes 0..7: the 8 lines of a trip, 4 trips ahead of the loads
-        uint32_t mpo = 6u * 1024u + lane * 128u + (lane < 8u ? 0u : 0x40000000u);
-#pragma unroll 1
+#pragma unroll 2
         for (uint32_t kb = 0; kb < m; kb += 32) {
             const uint32_t k = kb + lane;
-            if (mpo < mkBytes) prefetch_l2(mpf);
-            mpf += 1024; mpo += 1024;
-            const uint32_t kn = min(k + 64u, mm1);
-            const uint4 b0 = c0, b1 = c1;
-            c0 = __ldg(mq + 2 * kn); c1 = __ldg(mq + 2 * kn + 1);   // two trips ahead
+            if ((kb & 127u) == 0u) {                               // every 4th trip: the 32 lines of trips t+6 .. t+9 (1 KB per trip)
+                const uint32_t po = (kb + 192u) * 32u + lane * 128u;
+                if (po < mkBytes) prefetch_l2(reinterpret_cast<const char*>(mk) + po);
+            }
+            const uint32_t kn = min(k + 32u, mm1);
+            const uint4 b0 = __ldg(mq + 2 * kn), b1 = __ldg(mq + 2 * kn + 1);   // one trip ahead (L2 hits); unrolled by 2: no moves
             // a0 = {ctr, actor|kind<<16|bounds<<24, start_ctr, end_ctr}; a1 = {start_actor|end_actor<<16, attr, arrival, reserved}
             const uint32_t ctr = a0.x, actor = a0.y & 0xFFFFu, kind = (a0.y >> 16) & 0xFFu, bounds = a0.y >> 24;
             const uint32_t start_ctr = a0.z, end_ctr = a0.w, start_actor = a1.x & 0xFFFFu, end_actor = a1.x >> 16, attr = a1.y, arrival = a1.z;
@@ -787,7 +797,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
 //   free  : each warp takes kWarpGrab logs per atomic and runs on its own;
 //   phased: (warp_flags bit 2, the default) the CTA takes one log per warp per ROUND and its warps pass the phase barriers together
 //           (consecutive logs of the size-sorted queue are nearly the same size, so a round's warps finish together).
-template <int WARPS, bool COMPACT>
+template <int WARPS, int IDM>
 __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 1) merge_logs_warp_kernel(const BatchParams P) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_work = P.n_work;
@@ -831,7 +841,7 @@ __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 
             const uint32_t li = P.order[x];
             if (P.admit && P.admit[li]) { ps.leave(); continue; }      // rejected by the admission pre-pass
             const uint32_t li_next = xn < n_work ? P.order[xn] : 0xFFFFFFFFu;
-            const int rc = warp_merge_one_log<COMPACT>(P, li, base, slice, li_next, ps);   // the host put the log in the right launch
+            const int rc = warp_merge_one_log<IDM>(P, li, base, slice, li_next, ps);   // the host put the log in the right launch
             __syncwarp();
             if (rc) { if (lane == 0) P.retry_list[atomicAdd(P.retry_count, 1u)] = li; deferred++; } else done++;
         } else ps.leave();

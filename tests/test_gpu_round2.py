@@ -110,7 +110,7 @@ def test_warp_kernel_equals_block_kernel_equals_oracle(cfg, n_docs, ops):
     assert sa["logs_shared_only"] + sa["logs_spill_path"] == batch.n_logs
     assert sc["logs_deferred_to_big_bin"] > 0
     if cfg == "c4" and ops == 1000:
-        assert sa["logs_deferred_to_big_bin"] == 0            # the headline shape stays entirely on the warp kernel
+        assert sa["logs_deferred_to_big_bin"] <= batch.n_logs // 200    # the headline shape stays on the warp kernel (logs with > ~200 runs may defer)
 
 
 def test_warp_kernel_dense_surviving_marks_and_comments():
