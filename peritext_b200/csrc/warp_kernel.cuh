@@ -185,29 +185,28 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             const uint4 rc = ld_rec(ins + min(i + 32u, nm1));           // one trip ahead (the lines are in L2 by now); unrolled by 2: no moves
             const uint4 r = ra;
             const uint32_t ctr = r.x, ref_ctr = r.y, actor = r.z & 0xFFFFu, ref_actor = r.z >> 16, kind = r.w >> 30;
-            bool isIns = false, valid = false, toOv = false, wrote = false;
-            uint32_t key = 0, mine = 0;
-            if (i < n) {
-                if (kind > 1u) fail(PT_LOG_BAD_KIND);
-                else if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
-                else {
-                    valid = true; key = keyOf(ctr, actor);
-                    if (kind == PT_KIND_INSERT) {
-                        isIns = true;
-                        if (packed) {
-                            const uint32_t sh = 10u * actor;
-                            if ((atomicOr(&T32[ctr - 1u], (i + 1u) << sh) >> sh) & 1023u) fail(PT_LOG_BAD_OPID);   // two inserts with one opId
-                        } else if (!compact) {
-                            if (T[key] != kNone16) fail(PT_LOG_BAD_OPID);      // two inserts with one opId (earlier trip)
-                            T[key] = (uint16_t)i;
-                        } else {
-                            mine = (actor << 11) | i;
-                            const uint32_t e = T[ctr - 1u];
-                            if (e == kNone16) { T[ctr - 1u] = (uint16_t)mine; wrote = true; }
-                            else if ((e >> 11) == actor) fail(PT_LOG_BAD_OPID);
-                            else toOv = true;
-                        }
-                    }
+            // straight-line form: predicates instead of nested branches
+            const bool inb = i < n;
+            const bool kbad = kind > 1u, ibad = badId(ctr, actor);
+            const bool valid = inb && !kbad && !ibad;
+            if (inb && (kbad || ibad)) fail(kbad ? PT_LOG_BAD_KIND : PT_LOG_BAD_OPID);
+            const uint32_t key = keyOf(ctr, actor);
+            const bool isIns = valid && kind == PT_KIND_INSERT;
+            bool toOv = false, wrote = false;
+            uint32_t mine = 0;
+            if (isIns) {
+                if (packed) {
+                    const uint32_t sh = 10u * actor;
+                    if ((atomicOr(&T32[ctr - 1u], (i + 1u) << sh) >> sh) & 1023u) fail(PT_LOG_BAD_OPID);   // two inserts with one opId
+                } else if (!compact) {
+                    if (T[key] != kNone16) fail(PT_LOG_BAD_OPID);      // two inserts with one opId (earlier trip)
+                    T[key] = (uint16_t)i;
+                } else {
+                    mine = (actor << 11) | i;
+                    const uint32_t e = T[ctr - 1u];
+                    if (e == kNone16) { T[ctr - 1u] = (uint16_t)mine; wrote = true; }
+                    else if ((e >> 11) == actor) fail(PT_LOG_BAD_OPID);
+                    else toOv = true;
                 }
             }
             const uint32_t myK = isIns ? key : 0xFFFFFFFFu;
@@ -242,14 +241,17 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
                     __syncwarp();
                 }
             }
-            if (valid && !cand) {
-                if (ref_ctr == 0) { if (!isIns) fail(PT_LOG_ELEM_NOT_FOUND); }       // insert: child of HEAD
-                else {
-                    const uint32_t j = refOk ? lookup(ref_ctr, ref_actor) : kNone16;
-                    if (j == kNone16 || j >= i) fail(PT_LOG_ELEM_NOT_FOUND);           // must have arrived earlier
-                    else if (isIns && rkey >= key) fail(PT_LOG_CYCLE);
-                    else atomicOr(reinterpret_cast<uint32_t*>(&OD[j >> 5]) + (isIns ? 0u : 1u), 1u << (j & 31));   // deletes: OR, idempotent (micromerge.ts:689)
+            {   // B: the reference element of a non-chain record (ref_ctr == 0: an insert at the head of the list)
+                const bool need = valid && !cand, hasRef = ref_ctr != 0;
+                uint32_t j = kNone16;
+                if (need && refOk) j = lookup(ref_ctr, ref_actor);
+                const bool found = j != kNone16 && j < i;              // must have arrived earlier
+                const bool cyc = isIns && rkey >= key;
+                if (need) {
+                    if (hasRef ? !found : !isIns) fail(PT_LOG_ELEM_NOT_FOUND);
+                    else if (hasRef && cyc) fail(PT_LOG_CYCLE);
                 }
+                if (need && found && !cyc) atomicOr(reinterpret_cast<uint32_t*>(&OD[j >> 5]) + (isIns ? 0u : 1u), 1u << (j & 31));   // deletes: OR, idempotent (micromerge.ts:689)
             }
             ra = rc;
         }
@@ -298,29 +300,30 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         for (uint32_t o = lane * 128u; o < pfb; o += 32u * 128u) prefetch_l2(reinterpret_cast<const char*>(mk) + o);
     }
     // ---- D: run tree; E: Euler tour + splitter list ranking of the VISIBLE weights ------------------------------------------
-    const uint32_t E = 2 * (M + 1), END = E;
-    if (E + 1 >= 0xFFFFu) { ps.leave(); return 1; }
+    const uint32_t E = 2 * (M + 1), END = (E + 7u) & ~7u;          // END: terminator id, a multiple of 8 like every splitter node
+    if (END + 1 >= 0xFFFFu) { ps.leave(); return 1; }
     uint16_t* VisBase = A.alloc<uint16_t>(M + 1);                  // vis(i) = VisBase[run(i)] + visBefore(i)   (mod 2^16)
     const uint32_t markD = A.used;
     {
-        // Euler tour nodes: enter(r) = r, exit(r) = (M+1) + r, r in 0..M (M = HEAD).  Next[x]: successor (later: owner
-        // splitter); Wt[r]: visible weight of enter(r) (later: weight prefix inside the owner's sublist); exits weigh 0.
-        const uint32_t nSp = (E + 7) / 8 + 1, SPEND = nSp, KW = (KS + 31) / 32;
-        uint16_t* Next = A.alloc<uint16_t>(E + 1);
-        uint16_t* Wt = A.alloc<uint16_t>(M + 1);
+        // Euler tour nodes: enter(r) = r, exit(r) = (M+1) + r, r in 0..M (M = HEAD).  One 32-bit word per node: low half =
+        // successor (later: owner splitter), high half = visible weight of the node (later: weight prefix inside the owner's
+        // sublist); exits weigh 0.  Splitter ids: k < SPEND: node 8k; SPEND: the terminator; SPEND + 1: the tour's first node.
+        const uint32_t SPEND = END >> 3, nSp = SPEND + 2, KW = (KS + 31) / 32;
+        uint32_t* Node = A.alloc<uint32_t>(E);
+        uint16_t* N16 = reinterpret_cast<uint16_t*>(Node);         // N16[2x] = successor of x, N16[2x + 1] = weight of x
         uint16_t* HV = A.alloc<uint16_t>(M + 1);                   // run head record index, then visBefore(head)
         uint16_t* Prun = A.alloc<uint16_t>(M + 1);
         uint16_t* RKey = A.alloc<uint16_t>(M + 2);                 // key of the run head; dead after the ranking, then:
         uint16_t* Last = RKey;                                     // last threaded child of run q (q = M: HEAD)
         uint16_t* ByG = A.alloc<uint16_t>(M + 1);
         // key bitmap + prefix (ranking of the head keys); dead after the ranking, then the splitter summaries live there
-        const uint32_t uBytes = max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)(((nSp + 1) * 4 + 15) & ~15u));
+        const uint32_t uBytes = max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)((nSp * 4 + 15) & ~15u));
         char* U = A.alloc<char>(uBytes);
         if (!A.fits()) { ps.leave(); return 1; }
         uint32_t* KBits = reinterpret_cast<uint32_t*>(U);
         uint16_t* KPre = reinterpret_cast<uint16_t*>(U + (((KW + 1) * 4 + 15) & ~15u));
         uint32_t* Sub = reinterpret_cast<uint32_t*>(U);
-        uint32_t* Sub2 = reinterpret_cast<uint32_t*>(U + (((nSp + 1) * 4 + 15) & ~15u));
+        uint32_t* Sub2 = reinterpret_cast<uint32_t*>(U + ((nSp * 4 + 15) & ~15u));
 #pragma unroll 1
         for (uint32_t wb = 0; wb < NWr; wb += 32) {                // compact the run heads (one bit word per lane)
             const uint32_t w = wb + lane;
@@ -347,7 +350,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
                 const uint32_t p = rec.y == 0 ? n : lookup(rec.y, rec.z >> 16);
                 const uint32_t q = p == n ? M : runOf(p);
                 const uint32_t hv = visBefore(i);
-                Wt[r] = (uint16_t)(visBefore(end) - hv);
+                N16[2 * r + 1] = (uint16_t)(visBefore(end) - hv);
                 HV[r] = (uint16_t)hv;
                 Prun[r] = (uint16_t)q; RKey[r] = (uint16_t)key;
                 atomicOr(&KBits[key >> 5], 1u << (key & 31));
@@ -377,7 +380,6 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         __syncwarp();
         ps.pass();                                                 // (3) run heads ranked
         wfill<uint16_t>(Last, M + 2, (uint16_t)kNone16, lane);     // RKey, KBits, KPre are dead from here
-        if (lane == 0) { Sub[SPEND] = SPEND; Sub2[SPEND] = SPEND; }
         __syncwarp();
         // thread the runs in ASCENDING key order: among the children of one parent, the previously threaded one is the
         // NEXT sibling in descending-opId order (src/micromerge.ts:628-635), the last one threaded is the FIRST child
@@ -388,15 +390,15 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             const uint32_t r = valid ? (uint32_t)ByG[pos] : 0u;
             const uint32_t q = valid ? (uint32_t)Prun[r] : (0x10000u + lane);
             // MATCH.ANY costs a pass per distinct value; siblings inside one chunk are the exception, so probe first: every lane
-            // writes its lane id into a scratch slot of its parent (the enter half of Next, unused until the tour is built)
-            if (valid) Next[q] = (uint16_t)lane;
+            // writes its lane id into a scratch slot of its parent (the successor half of the enter nodes, unused until the tour is built)
+            if (valid) N16[2 * q] = (uint16_t)lane;
             __syncwarp();
-            const bool lost = valid && Next[q] != lane;
+            const bool lost = valid && N16[2 * q] != lane;
             uint32_t mask = 1u << lane;
             if (__any_sync(kFull, lost)) {                         // only the lanes of clashing parents enter MATCH.ANY
-                if (lost) Next[q] = (uint16_t)kNone16;
+                if (lost) N16[2 * q] = (uint16_t)kNone16;
                 __syncwarp();
-                const bool grouped = valid && Next[q] == kNone16;
+                const bool grouped = valid && N16[2 * q] == kNone16;
                 const uint32_t pm = __ballot_sync(kFull, grouped);
                 if (grouped) mask = __match_any_sync(pm, q);
             }
@@ -407,7 +409,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             if (valid) ns = lower ? rs : (uint32_t)Last[q];
             __syncwarp();
             if (valid) {
-                Next[(M + 1) + r] = (uint16_t)(ns != kNone16 ? ns : (M + 1) + q);   // exit(r): next sibling, else exit(parent)
+                Node[(M + 1) + r] = ns != kNone16 ? ns : (M + 1) + q;               // exit(r): next sibling, else exit(parent); weight 0
                 if (((mask >> lane) >> 1) == 0) Last[q] = (uint16_t)r;              // highest lane of its group
             }
             __syncwarp();
@@ -415,31 +417,31 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
 #pragma unroll 1
         for (uint32_t rb = 0; rb <= M; rb += 32) {                 // enter(r): first child, else exit(r)
             const uint32_t r = rb + lane;
-            if (r <= M) { const uint32_t f = Last[r]; Next[r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); }
+            if (r <= M) { const uint32_t f = Last[r]; N16[2 * r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); }
         }
-        if (lane == 0) { Wt[M] = 0; Next[(M + 1) + M] = (uint16_t)END; Next[END] = (uint16_t)END; }
+        if (lane == 0) { N16[2 * M + 1] = 0; Node[(M + 1) + M] = END; }
         __syncwarp();
         // splitter list ranking: every 8th node id (and the tour's first node) walks its sublist once; only the splitter
         // summaries are ranked by pointer jumping; suffix(x) = suffix(owner sublist) - prefix(x)
+        // (no node's successor is the tour's first node, and END is a multiple of 8: a sublist ends where the successor id is)
         const uint32_t headNode = M;
-        auto spOf = [&](uint32_t x) -> uint32_t { return (x & 7u) == 0 ? (x >> 3) : nSp - 1; };
-        auto isSp = [&](uint32_t x) -> bool { return (x & 7u) == 0 || x == headNode; };
 #pragma unroll 1
         for (uint32_t kb = 0; kb < nSp; kb += 32) {
             const uint32_t k = kb + lane;
             if (k < nSp) {
-                uint32_t cur = k + 1 < nSp ? 8 * k : headNode, acc = 0, nx = END;
-                const bool valid = cur < E && (k + 1 < nSp || (headNode & 7u) != 0);
+                uint32_t cur = k < SPEND ? 8 * k : headNode, acc = 0, nx = END;
+                const bool valid = k < SPEND ? cur < E : (k > SPEND && (headNode & 7u) != 0);
                 if (valid) {
                     for (;;) {
-                        nx = Next[cur];
-                        Next[cur] = (uint16_t)k;                   // owner
-                        if (cur <= M) { const uint32_t wv = Wt[cur]; Wt[cur] = (uint16_t)acc; acc += wv; }   // prefix before this node
-                        if (nx == END || isSp(nx)) break;
+                        const uint32_t a = Node[cur];
+                        nx = a & 0xFFFFu;
+                        Node[cur] = k | (acc << 16);               // owner | weight prefix before this node
+                        acc += a >> 16;
+                        if ((nx & 7u) == 0) break;
                         cur = nx;
                     }
                 }
-                Sub[k] = valid ? ((acc << 16) | (nx == END ? SPEND : spOf(nx))) : SPEND;
+                Sub[k] = (acc << 16) | (nx >> 3);                  // invalid / terminator entries: weight 0, successor SPEND
             }
         }
         __syncwarp();
@@ -460,7 +462,8 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         for (uint32_t rb = 0; rb < M; rb += 32) {
             const uint32_t r = rb + lane;
             if (r < M) {
-                const uint32_t suf = (Sub[Next[r]] >> 16) - (uint32_t)Wt[r];        // visible elements from run r to the end
+                const uint32_t a = Node[r];
+                const uint32_t suf = (Sub[a & 0xFFFFu] >> 16) - (a >> 16);          // visible elements from run r to the end
                 VisBase[r] = (uint16_t)((nvis - suf) - (uint32_t)HV[r]);
             }
         }
@@ -537,33 +540,34 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             const uint32_t ctr = a0.x, actor = a0.y & 0xFFFFu, kind = (a0.y >> 16) & 0xFFu, bounds = a0.y >> 24;
             const uint32_t start_ctr = a0.z, end_ctr = a0.w, start_actor = a1.x & 0xFFFFu, end_actor = a1.x >> 16, attr = a1.y, arrival = a1.z;
             const uint32_t type = (kind >> 1) & 3u;
-            bool surv = false;
-            uint32_t va = 0, vb = 0, key = 0;
-            if (k < m) {
-                if (badId(ctr, actor)) fail(PT_LOG_BAD_OPID);
-                else {
-                    key = keyOf(ctr, actor);
-                    const uint32_t bit = 1u << (key & 31);
-                    if ((atomicOr(&KBits[key >> 5], bit) & bit) || lookup(ctr, actor) != kNone16) fail(PT_LOG_BAD_OPID);   // duplicate opId
-                    const uint32_t sb = bounds & 3u, eb = (bounds >> 2) & 3u;
-                    // a boundary element must exist AND have arrived before the mark op: the reference's walk never matches
-                    // anything else (peritext.ts:236-241) — a missing start is a no-op, a missing end never ends
-                    if (sb <= PT_BOUND_AFTER && !badId(start_ctr, start_actor)) {
-                        const uint32_t js = lookup(start_ctr, start_actor);
-                        if (js != kNone16 && js < arrival) {
-                            const uint32_t es = EV[js];
-                            va = (es & 0x7FFFu) + (sb & (es >> 15));
-                            vb = nvis;
-                            if (eb <= PT_BOUND_AFTER && !badId(end_ctr, end_actor)) {
-                                const uint32_t je = lookup(end_ctr, end_actor);
-                                // same slot: the start branch wins and the op never ends (quirk Q2)
-                                if (je != kNone16 && je < arrival && !(je == js && eb == sb)) { const uint32_t ee = EV[je]; vb = (ee & 0x7FFFu) + (eb & (ee >> 15)); }
-                            }
-                            surv = va < vb;
-                        }
-                    }
-                }
+            // straight-line form (predicated loads instead of nested branches).  A boundary element must exist AND have arrived
+            // before the mark op: the reference's walk never matches anything else (peritext.ts:236-241) — a missing start is a
+            // no-op, a missing end never ends
+            const bool inb = k < m;
+            const bool idok = inb && !badId(ctr, actor);
+            const uint32_t key = keyOf(ctr, actor);
+            bool dup = false;
+            if (idok) {
+                const uint32_t bit = 1u << (key & 31);
+                dup = (atomicOr(&KBits[key >> 5], bit) & bit) != 0 || lookup(ctr, actor) != kNone16;      // duplicate opId
             }
+            if (inb && (!idok || dup)) fail(PT_LOG_BAD_OPID);
+            const uint32_t sb = bounds & 3u, eb = (bounds >> 2) & 3u;
+            const bool sOk = idok && sb <= PT_BOUND_AFTER && !badId(start_ctr, start_actor);
+            uint32_t js = kNone16;
+            if (sOk) js = lookup(start_ctr, start_actor);
+            const bool sHit = js != kNone16 && js < arrival;
+            uint32_t es = 0;
+            if (sHit) es = EV[js];
+            const uint32_t va = (es & 0x7FFFu) + (sb & (es >> 15));
+            const bool eOk = sHit && eb <= PT_BOUND_AFTER && !badId(end_ctr, end_actor);
+            uint32_t je = kNone16;
+            if (eOk) je = lookup(end_ctr, end_actor);
+            // same slot: the start branch wins and the op never ends (quirk Q2)
+            const bool eHit = je != kNone16 && je < arrival && !(je == js && eb == sb);
+            uint32_t vb = nvis;
+            if (eHit) { const uint32_t ee = EV[je]; vb = (ee & 0x7FFFu) + (eb & (ee >> 15)); }
+            const bool surv = sHit && va < vb;
             const bool isC = surv && type == PT_MARK_COMMENT;
             const uint32_t bal = __ballot_sync(kFull, surv), balC = __ballot_sync(kFull, isC);
             if (surv) {
