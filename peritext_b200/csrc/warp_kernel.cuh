@@ -315,7 +315,8 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         uint16_t* Prun = A.alloc<uint16_t>(M + 1);
         uint16_t* RKey = A.alloc<uint16_t>(M + 2);                 // key of the run head; dead after the ranking, then:
         uint16_t* Last = RKey;                                     // last threaded child of run q (q = M: HEAD)
-        uint16_t* ByG = A.alloc<uint16_t>(M + 1);
+        // ByG[pos] (run with the pos-th smallest head key) lives in the weight halves of the exit nodes until the tour is threaded
+        auto ByG = [&](uint32_t pos) -> uint16_t& { return N16[2 * ((M + 1) + pos) + 1]; };
         // key bitmap + prefix (ranking of the head keys); dead after the ranking, then the splitter summaries live there
         const uint32_t uBytes = max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)((nSp * 4 + 15) & ~15u));
         char* U = A.alloc<char>(uBytes);
@@ -374,7 +375,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             const uint32_t r = rb + lane;
             if (r < M) {
                 const uint32_t key = RKey[r];
-                ByG[(uint32_t)KPre[key >> 5] + __popc(KBits[key >> 5] & ((1u << (key & 31)) - 1u))] = (uint16_t)r;
+                ByG((uint32_t)KPre[key >> 5] + __popc(KBits[key >> 5] & ((1u << (key & 31)) - 1u))) = (uint16_t)r;
             }
         }
         __syncwarp();
@@ -387,7 +388,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         for (uint32_t cb = 0; cb < M; cb += 32) {
             const uint32_t pos = cb + lane;
             const bool valid = pos < M;
-            const uint32_t r = valid ? (uint32_t)ByG[pos] : 0u;
+            const uint32_t r = valid ? (uint32_t)ByG(pos) : 0u;
             const uint32_t q = valid ? (uint32_t)Prun[r] : (0x10000u + lane);
             // MATCH.ANY costs a pass per distinct value; siblings inside one chunk are the exception, so probe first: every lane
             // writes its lane id into a scratch slot of its parent (the successor half of the enter nodes, unused until the tour is built)
@@ -409,7 +410,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             if (valid) ns = lower ? rs : (uint32_t)Last[q];
             __syncwarp();
             if (valid) {
-                Node[(M + 1) + r] = ns != kNone16 ? ns : (M + 1) + q;               // exit(r): next sibling, else exit(parent); weight 0
+                N16[2 * ((M + 1) + r)] = (uint16_t)(ns != kNone16 ? ns : (M + 1) + q);   // exit(r): next sibling, else exit(parent)
                 if (((mask >> lane) >> 1) == 0) Last[q] = (uint16_t)r;              // highest lane of its group
             }
             __syncwarp();
@@ -417,7 +418,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
 #pragma unroll 1
         for (uint32_t rb = 0; rb <= M; rb += 32) {                 // enter(r): first child, else exit(r)
             const uint32_t r = rb + lane;
-            if (r <= M) { const uint32_t f = Last[r]; N16[2 * r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); }
+            if (r <= M) { const uint32_t f = Last[r]; N16[2 * r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); N16[2 * ((M + 1) + r) + 1] = 0; }   // exits weigh 0 (ByG is dead)
         }
         if (lane == 0) { N16[2 * M + 1] = 0; Node[(M + 1) + M] = END; }
         __syncwarp();
@@ -602,6 +603,83 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
     } else {
         // ---- I: elementary segments of the visible text -> marks per segment -> spans ---------------------------------------
         if (nC > kMaxCommentSurvivors) { ps.leave(); return 1; }
+        if (nvis <= 32u && nC <= 32u) {
+            // ---- I (short text): at most 32 visible characters: one lane per visible POSITION instead of elementary segments — no
+            // boundary bitmap, no segment arrays.  Marks / link / comment-id set per position; a span starts where any of them
+            // differs from the position before (same result as the segment form below: nothing changes inside a segment).
+            const uint32_t x = lane;
+            uint32_t w0 = 0, w1 = 0, w2 = 0, flags = 0, link = PT_ATTR_NONE;
+#pragma unroll 1
+            for (uint32_t j = 0; j < nS; j++) {
+                const uint4 sv = Sv[j];                              // one broadcast LDS.128
+                const uint32_t ab = sv.x, pk = sv.y;
+                const bool cover = x >= (ab & 0xFFFFu) && x < (ab >> 16);
+                const uint32_t t = (pk >> 17) & 3u, val = (((pk & 0xFFFFu) << 16) | j) + 1u;
+                if (cover) {
+                    if (t == PT_MARK_STRONG) w0 = max(w0, val);
+                    else if (t == PT_MARK_EM) w1 = max(w1, val);
+                    else if (t == PT_MARK_LINK) w2 = max(w2, val);
+                    else flags |= PT_SPAN_COMMENT;                   // `comment` key present iff any comment op covers (quirk Q3)
+                }
+            }
+            // LWW winners (peritext.ts:304-313): the max-opId covering op of the type; present iff it is an addMark
+            if (w0 && !((Sv[(w0 - 1u) & 0xFFFFu].y >> 16) & 1u)) flags |= PT_SPAN_STRONG;
+            if (w1 && !((Sv[(w1 - 1u) & 0xFFFFu].y >> 16) & 1u)) flags |= PT_SPAN_EM;
+            if (w2) { const uint32_t j2 = (w2 - 1u) & 0xFFFFu; if (!((Sv[j2].y >> 16) & 1u)) { flags |= PT_SPAN_LINK; link = Sv[j2].z; } }
+            // comment ids present at x: ids whose last-arrived covering op is an add (peritext.ts:314-322); the set is a bit mask
+            // over the surviving comment ops, an id being named by the FIRST surviving op that carries it
+            uint32_t cmask = 0;
+            if (nC) {
+                uint32_t canon = lane;
+                if (lane < nC) {
+                    const uint32_t id = Sv[CIdx[lane]].z;
+                    for (uint32_t c0 = 0; c0 < lane; c0++) if (Sv[CIdx[c0]].z == id) { canon = c0; break; }
+                }
+#pragma unroll 1
+                for (uint32_t cj = 0; cj < nC; cj++) {
+                    const uint4 s1 = Sv[CIdx[cj]];                   // uniform
+                    const uint32_t rep = __shfl_sync(kFull, canon, cj);
+                    const bool cov = x >= (s1.x & 0xFFFFu) && x < (s1.x >> 16);
+                    if (!__any_sync(kFull, cov)) continue;
+                    bool later = false;
+                    for (uint32_t c2 = cj + 1; c2 < nC; c2++) {
+                        const uint4 s2 = Sv[CIdx[c2]];
+                        if (s2.z != s1.z) continue;                  // uniform
+                        if (x >= (s2.x & 0xFFFFu) && x < (s2.x >> 16)) later = true;
+                    }
+                    if (cov && !later && !((s1.y >> 16) & 1u)) cmask |= 1u << rep;
+                }
+            }
+            const uint32_t pf = __shfl_up_sync(kFull, flags, 1), pl = __shfl_up_sync(kFull, link, 1), pm = __shfl_up_sync(kFull, cmask, 1);
+            const bool head = x < nvis && (x == 0 || ((flags ^ pf) & 0xFu) != 0 || link != pl || cmask != pm);
+            const uint32_t hb = __ballot_sync(kFull, head);
+            const uint32_t cnt = head ? (uint32_t)__popc(cmask) : 0u;
+            const uint32_t inc = warp_incl_scan(cnt, lane), off = inc - cnt, totalC = __shfl_sync(kFull, inc, 31);
+            nspans = __popc(hb);
+            if (totalC) {
+                uint32_t pst = 0;
+                if (lane == 0) pool_base = pool_reserve(P, totalC, pst);
+                pst = __shfl_sync(kFull, pst, 0);
+                if (pst) { bail(pst); ps.leave(); return 0; }
+                pool_base = __shfl_sync(kFull, pool_base, 0);
+            }
+            if (head) {
+                const uint32_t jo = __popc(hb & lt);
+                uint32_t* pool = P.comment_pool + pool_base;
+                uint32_t filled = 0;
+                for (uint32_t mm = cmask; mm; mm &= mm - 1u) {       // ascending id order (sortBy, peritext.ts:318); the lists are short
+                    const uint32_t id = Sv[CIdx[__ffs(mm) - 1]].z;
+                    uint32_t y = filled;
+                    while (y > 0 && pool[off + y - 1] > id) { pool[off + y] = pool[off + y - 1]; y--; }
+                    pool[off + y] = id; filled++;
+                }
+                pt_span sp; sp.start = x; sp.flags = (flags & 0xFu) | (cnt << 8); sp.link_attr = link;
+                sp.comment_off = cnt ? (uint32_t)(pool_base + off) : 0u;
+                span_out[jo] = sp;
+                for (uint32_t y = 0; y < cnt; y++) digest_add(d0, d1, pt_term_comment(jo, y, pool[off + y]));
+                digest_add(d0, d1, pt_term_span(jo, sp.start, sp.flags, sp.link_attr));
+            }
+        } else {
         const uint32_t BW = nvis / 32 + 1;
         uint32_t* Bnd = A.alloc<uint32_t>(BW + 1);
         uint16_t* BPre = A.alloc<uint16_t>(BW + 1);
@@ -782,6 +860,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
                 digest_add(d0, d1, pt_term_span(jo, sp.start, sp.flags, sp.link_attr));
             }
         }
+        }   // segment form
     }
 
 #pragma unroll
