@@ -107,10 +107,10 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
     }
 
     WArena A; A.base = slice_base; A.used = 0; A.cap = slice_bytes;
-    uint32_t st = 0;                                           // lane-local status, max-reduced at the checkpoints
+    uint32_t st = 0;                                           // lane-local failures, bit (1 << code); the checkpoints report the highest code
     auto keyOf = [&](uint32_t ctr, uint32_t actor) -> uint32_t { return (ctr - 1u) * R + actor; };
     auto badId = [&](uint32_t ctr, uint32_t actor) -> bool { return ctr - 1u >= C || actor >= R; };
-    auto fail = [&](uint32_t code) { st = max(st, code); };
+    auto fail = [&](uint32_t code) { st |= 1u << code; };
     auto bail = [&](uint32_t code) { if (lane == 0) { pt_log_result r{}; r.status = code; *res = r; } };
 
     // ---- id table: opId -> insert record index ------------------------------------------------------------------------------
@@ -134,14 +134,12 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
     uint4* WI = A.alloc<uint4>(NWr);
     uint16_t* T = A.alloc<uint16_t>(packed ? 2u * C : compact ? C : KS);
     uint32_t* T32 = reinterpret_cast<uint32_t*>(T);              // packed3 view
-    const uint32_t markC = A.used;
-    uint2* OD = A.alloc<uint2>(NWr);                           // x = element has a child that is not its log successor, y = tombstone (dead after C)
     if (!A.fits()) { ps.leave(); return 1; }
     if (packed) wfill<uint32_t>(T32, C, 0u, lane);
     else wfill<uint16_t>(T, compact ? C : KS, (uint16_t)kNone16, lane);
     if (compact) wfill<uint32_t>(OV, kOvSlots, kOvEmpty, lane);
-    wfill<uint32_t>(reinterpret_cast<uint32_t*>(OD), 2 * NWr, 0u, lane);
-    if (lane == 0) WI[NWr - 1] = make_uint4(0, 0, 0, 0);
+    // during A+B the z / w fields of WI collect the "element has a child that is not its log successor" and tombstone bits (atomicOr)
+    wfill<uint32_t>(reinterpret_cast<uint32_t*>(WI), 4 * NWr, 0u, lane);
     __syncwarp();
     auto ovHash = [&](uint32_t key) -> uint32_t { return ((key * 40503u) >> 7) & (kOvSlots - 1u); };
     // index of the insert record with opId (ctr, actor), kNone16 if there is none; the id must be in range (!badId)
@@ -189,7 +187,8 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             const bool inb = i < n;
             const bool kbad = kind > 1u, ibad = badId(ctr, actor);
             const bool valid = inb && !kbad && !ibad;
-            if (inb && (kbad || ibad)) fail(kbad ? PT_LOG_BAD_KIND : PT_LOG_BAD_OPID);
+            if (inb && kbad) fail(PT_LOG_BAD_KIND);
+            if (inb && ibad) fail(PT_LOG_BAD_OPID);
             const uint32_t key = keyOf(ctr, actor);
             const bool isIns = valid && kind == PT_KIND_INSERT;
             bool toOv = false, wrote = false;
@@ -251,7 +250,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
                     if (hasRef ? !found : !isIns) fail(PT_LOG_ELEM_NOT_FOUND);
                     else if (hasRef && cyc) fail(PT_LOG_CYCLE);
                 }
-                if (need && found && !cyc) atomicOr(reinterpret_cast<uint32_t*>(&OD[j >> 5]) + (isIns ? 0u : 1u), 1u << (j & 31));   // deletes: OR, idempotent (micromerge.ts:689)
+                if (need && found && !cyc) atomicOr(reinterpret_cast<uint32_t*>(&WI[j >> 5]) + (isIns ? 2u : 3u), 1u << (j & 31));   // deletes: OR, idempotent (micromerge.ts:689)
             }
             ra = rc;
         }
@@ -259,8 +258,8 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
     __syncwarp();
     ps.pass();                                                     // (2) end of the record pass
     if (compact && nOv > kOvMax) { ps.leave(); return 1; }                                    // too many concurrent-counter inserts for the compact table
-    st = __reduce_max_sync(kFull, st);
-    if (st) { bail(st); ps.leave(); return 0; }
+    st = __reduce_or_sync(kFull, st);
+    if (st) { bail(31u - __clz(st)); ps.leave(); return 0; }
 
     // ---- C: runs, bit-parallel: head = insert & (!chain-link | predecessor has another child); visible = insert & !deleted
     uint32_t M, nvis, N = 0;
@@ -269,7 +268,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         for (uint32_t wb = 0; wb < NWr; wb += 32) {
             const uint32_t w = wb + lane;
             uint32_t insW = 0, candW = 0, otherW = 0, delW = 0;
-            if (w < NWr) { const uint2 ic = *reinterpret_cast<const uint2*>(&WI[w]); const uint2 od = OD[w]; insW = ic.x; candW = ic.y; otherW = od.x; delW = od.y; }
+            if (w < NWr) { const uint4 q = WI[w]; insW = q.x; candW = q.y; otherW = q.z; delW = q.w; }
             const uint32_t up = __shfl_up_sync(kFull, otherW, 1);
             const uint32_t prevBit = lane ? (up >> 31) : otherCarry;
             otherCarry = __shfl_sync(kFull, otherW, 31) >> 31;
@@ -283,7 +282,6 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         }
         M = carryH; nvis = carryV;
     }
-    A.used = markC;                                                // release OD
     __syncwarp();
 
     auto runOf = [&](uint32_t i) -> uint32_t {
@@ -295,6 +293,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
         return (q.w >> 16) + __popc(q.z & ((1u << (i & 31)) - 1u));
     };
 
+    if ((P.warp_flags & 2u) && li_next != 0xFFFFFFFFu && lane == 0) prefetch_l2(P.desc + li_next);   // read in phase F
     if (m) {       // the first 6 trips of mark records (needed in phase G) start their way to L2 now
         const uint32_t pfb = min(m * 32u, 6u * 1024u);
         for (uint32_t o = lane * 128u; o < pfb; o += 32u * 128u) prefetch_l2(reinterpret_cast<const char*>(mk) + o);
@@ -583,8 +582,8 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             a0 = b0; a1 = b1;
         }
         __syncwarp();
-        st = __reduce_max_sync(kFull, st);
-        if (st) { bail(st); ps.leave(); return 0; }
+        st = __reduce_or_sync(kFull, st);
+        if (st) { bail(31u - __clz(st)); ps.leave(); return 0; }
         if (nS > capS) { ps.leave(); return 1; }
         A.used = svStart + ((nS * 16u + 15u) & ~15u);               // keep only the survivors
     }
@@ -889,11 +888,11 @@ __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 
     asm volatile("" : "+r"(base));         // opaque: keep it in a register instead of re-deriving it from threadIdx at every shared-memory access
     uint32_t done = 0, deferred = 0;
     const bool phased = (P.warp_flags & 4u) != 0;
-    __shared__ uint32_t s_base[2];
+    __shared__ uint32_t s_base[2], s_nxt[2];
     PhaseSync ps; ps.on = phased ? 1u : 0u; ps.nthreads = WARPS * 32; ps.next = kFirstPhaseBar; ps.skip = (P.warp_flags >> 8) & 0xFu;
-    uint32_t nextb = 0, par = 0;           // phased: the CTA's next round (held by thread 0)
+    uint32_t nextb = 0, nextb2 = 0, par = 0;   // phased: the CTA's next two rounds (held by thread 0)
     uint32_t w = 0, wend = 0, wn = 0;      // free: this warp's current grab [w, wend) and the next one
-    if (phased) { if (threadIdx.x == 0) nextb = atomicAdd(P.work_counter, (uint32_t)WARPS); }
+    if (phased) { if (threadIdx.x == 0) { nextb = atomicAdd(P.work_counter, (uint32_t)WARPS); nextb2 = atomicAdd(P.work_counter, (uint32_t)WARPS); } }
     else {
         if (lane == 0) { w = atomicAdd(P.work_counter, kWarpGrab); wn = atomicAdd(P.work_counter, kWarpGrab); }
         w = __shfl_sync(kFull, w, 0); wn = __shfl_sync(kFull, wn, 0);
@@ -902,12 +901,14 @@ __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 
     for (;;) {
         uint32_t x, xn = 0xFFFFFFFFu;
         if (phased) {
-            if (threadIdx.x == 0) { s_base[par] = nextb; nextb = atomicAdd(P.work_counter, (uint32_t)WARPS); }
+            // the round after this one is known too (fetched a round ago): its logs' records can be on their way to L2
+            if (threadIdx.x == 0) { s_base[par] = nextb; s_nxt[par] = nextb2; nextb = nextb2; nextb2 = atomicAdd(P.work_counter, (uint32_t)WARPS); }
             asm volatile("barrier.sync 1, %0;" ::"r"((uint32_t)(WARPS * 32)) : "memory");
-            const uint32_t b0 = s_base[par];
+            const uint32_t b0 = s_base[par], bn = s_nxt[par];
             par ^= 1u;
             if (b0 >= n_work) break;
             x = b0 + warp;
+            xn = bn + warp;
             ps.next = kFirstPhaseBar;
         } else {
             if (w >= wend) {
@@ -923,7 +924,7 @@ __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 
         if (x < n_work) {
             const uint32_t li = P.order[x];
             if (P.admit && P.admit[li]) { ps.leave(); continue; }      // rejected by the admission pre-pass
-            const uint32_t li_next = xn < n_work ? P.order[xn] : 0xFFFFFFFFu;
+            const uint32_t li_next = ((P.warp_flags & 2u) && xn < n_work) ? P.order[xn] : 0xFFFFFFFFu;
             const int rc = warp_merge_one_log<IDM>(P, li, base, slice, li_next, ps);   // the host put the log in the right launch
             __syncwarp();
             if (rc) { if (lane == 0) P.retry_list[atomicAdd(P.retry_count, 1u)] = li; deferred++; } else done++;
