@@ -960,7 +960,7 @@ static int enqueue_merge(pt_batch* b) {
         P.admit = (const uint32_t*)b->d_admit.p;
     }
     { const char* e = getenv("PT_PREFETCH"); P.prefetch_next = e ? (uint32_t)atoi(e) : 0u; }
-    { const char* e = getenv("PT_WARP_FLAGS"); P.warp_flags = e ? (uint32_t)atoi(e) : 4u; }   // default: phase-aligned warps, no L2 prefetch
+    { const char* e = getenv("PT_WARP_FLAGS"); P.warp_flags = e ? (uint32_t)atoi(e) : 0x704u; }   // default: phase-aligned rounds (bit 2), the in-log phase barriers 2-4 skipped (bits 8-10: measured), no extra L2 prefetch
     { const char* e = getenv("PT_TMA"); P.use_tma = e ? (uint32_t)atoi(e) : 1u; }
     int rc;
     // ascending bins; a log whose working set does not fit bin k's shared memory is deferred (on the device) to bin k+1;
