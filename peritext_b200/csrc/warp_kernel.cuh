@@ -389,16 +389,19 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             const bool valid = pos < M;
             const uint32_t r = valid ? (uint32_t)ByG(pos) : 0u;
             const uint32_t q = valid ? (uint32_t)Prun[r] : (0x10000u + lane);
-            // MATCH.ANY costs a pass per distinct value; siblings inside one chunk are the exception, so probe first: every lane
-            // writes its lane id into a scratch slot of its parent (the successor half of the enter nodes, unused until the tour is built)
-            if (valid) N16[2 * q] = (uint16_t)lane;
-            __syncwarp();
-            const bool lost = valid && N16[2 * q] != lane;
+            // MATCH.ANY costs a pass per distinct value; siblings inside one chunk are the exception, so probe first: the successor
+            // half of the parent's enter node is scratch until the tour is built.  Every lane reads its parent's word, then tries to
+            // flip bit 0 of it with a CAS: the first lane per parent succeeds, a sibling in the same chunk sees the change.
+            uint32_t o = 0;
+            if (valid) o = Node[q];
+            __syncwarp();                                          // all reads before the first change
+            bool lost = false;
+            if (valid) lost = atomicCAS(&Node[q], o, o ^ 1u) != o;
             uint32_t mask = 1u << lane;
             if (__any_sync(kFull, lost)) {                         // only the lanes of clashing parents enter MATCH.ANY
-                if (lost) N16[2 * q] = (uint16_t)kNone16;
+                if (lost) atomicOr(&Node[q], 0xFFFFu);
                 __syncwarp();
-                const bool grouped = valid && N16[2 * q] == kNone16;
+                const bool grouped = valid && (Node[q] & 0xFFFFu) == 0xFFFFu;
                 const uint32_t pm = __ballot_sync(kFull, grouped);
                 if (grouped) mask = __match_any_sync(pm, q);
             }
