@@ -194,8 +194,7 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
     const uint32_t uBytes = max(max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)(((nSp + 1) * 4 + 15) & ~15u)),
                                 (uint32_t)(((M + 32) * 2 + 15) & ~15u));
     char* U = A.alloc<char>(uBytes);     // successively: key bitmap + prefix | per-warp run lists of the threading | splitter summaries
-    if (!A.fits() || 2ull * (M + 2) > KS) return 1;
-    uint32_t* Probe = reinterpret_cast<uint32_t*>(T);             // threading scratch, one word per parent: the id table is dead after the parent lookups
+    if (!A.fits()) return 1;
     uint32_t* KBits = reinterpret_cast<uint32_t*>(U);
     uint16_t* KPre = reinterpret_cast<uint16_t*>(U + (((KW + 1) * 4 + 15) & ~15u));
     uint32_t* Sub = reinterpret_cast<uint32_t*>(U);
@@ -276,22 +275,10 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
             const bool valid = pos < mine;
             const uint32_t r = valid ? (uint32_t)Lst[off + pos] : 0u;
             const uint32_t q = valid ? (uint32_t)Prun[r] : (0x10000u + lane);
-            // MATCH.ANY costs a pass per distinct value; siblings inside one chunk are rare, so probe first: every lane reads its
-            // parent's scratch word, then tries to flip bit 0 of it with a CAS: the first lane per parent succeeds, a sibling in the
-            // same chunk sees the change (parents are dealt to the warps by q % TEAM: a word is only ever touched by one warp)
-            uint32_t o = 0;
-            if (valid) o = Probe[q];
-            __syncwarp();                                          // all reads before the first change
-            bool lost = false;
-            if (valid) lost = atomicCAS(&Probe[q], o, o ^ 1u) != o;
+            // siblings inside this chunk of 32: MATCH.ANY over the parents (measured: cheaper than any probe that would avoid it)
             uint32_t mask = 1u << lane;
-            if (__any_sync(kFull, lost)) {                         // only the lanes of clashing parents enter MATCH.ANY
-                if (lost) atomicOr(&Probe[q], 0xFFFFu);
-                __syncwarp();
-                const bool grouped = valid && (Probe[q] & 0xFFFFu) == 0xFFFFu;
-                const uint32_t pm = __ballot_sync(kFull, grouped);
-                if (grouped) mask = __match_any_sync(pm, q);
-            }
+            const uint32_t pm = __ballot_sync(kFull, valid);
+            if (valid) mask = __match_any_sync(pm, q);
             const uint32_t lower = mask & lt;
             const uint32_t src = lower ? (31u - __clz(lower)) : lane;
             const uint32_t rs = __shfl_sync(kFull, r, src);

@@ -389,27 +389,10 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
             const bool valid = pos < M;
             const uint32_t r = valid ? (uint32_t)ByG(pos) : 0u;
             const uint32_t q = valid ? (uint32_t)Prun[r] : (0x10000u + lane);
-            // MATCH.ANY costs a pass per distinct value; siblings inside one chunk are the exception, so probe first: the successor
-            // half of the parent's enter node is scratch until the tour is built.  Every lane reads its parent's word, then tries to
-            // flip bit 0 of it with a CAS: the first lane per parent succeeds, a sibling in the same chunk sees the change.
+            // siblings inside this chunk of 32: MATCH.ANY over the parents (measured: cheaper than any probe that would avoid it)
             uint32_t mask = 1u << lane;
-            if (P.warp_flags & 8u) {                               // (tuning: MATCH.ANY over the whole chunk, no probe)
-                const uint32_t pm = __ballot_sync(kFull, valid);
-                if (valid) mask = __match_any_sync(pm, q);
-            } else {
-            uint32_t o = 0;
-            if (valid) o = Node[q];
-            __syncwarp();                                          // all reads before the first change
-            bool lost = false;
-            if (valid) lost = atomicCAS(&Node[q], o, o ^ 1u) != o;
-            if (__any_sync(kFull, lost)) {                         // only the lanes of clashing parents enter MATCH.ANY
-                if (lost) atomicOr(&Node[q], 0xFFFFu);
-                __syncwarp();
-                const bool grouped = valid && (Node[q] & 0xFFFFu) == 0xFFFFu;
-                const uint32_t pm = __ballot_sync(kFull, grouped);
-                if (grouped) mask = __match_any_sync(pm, q);
-            }
-            }
+            const uint32_t pm = __ballot_sync(kFull, valid);
+            if (valid) mask = __match_any_sync(pm, q);
             const uint32_t lower = mask & lt;
             const uint32_t src = lower ? (31u - __clz(lower)) : lane;
             const uint32_t rs = __shfl_sync(kFull, r, src);
