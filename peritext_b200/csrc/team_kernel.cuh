@@ -180,25 +180,28 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
     auto visBefore = [&](uint32_t i) -> uint32_t { const uint4 q = WI[i >> 5]; return (q.w >> 16) + __popc(q.z & ((1u << (i & 31)) - 1u)); };
 
     // ---- D: run tree; E: Euler tour + splitter ranking of the visible weights -------------------------------------------------
-    const uint32_t E = 2 * (M + 1), END = E;
-    if (E + 1 >= 0xFFFFu) return 1;
-    const uint32_t nSp = (E + 7) / 8 + 1, SPEND = nSp, KW = (KS + 31) / 32;
-    uint16_t* Next = A.alloc<uint16_t>(E + 1);
-    uint16_t* Wt = A.alloc<uint16_t>(M + 1);
+    // tour nodes as in warp_kernel.cuh: one 32-bit word per node (successor | visible weight; later owner splitter | weight prefix);
+    // END (terminator id) is a multiple of 8 like every splitter node; splitter ids: k < SPEND: node 8k; SPEND: terminator; SPEND + 1: head
+    const uint32_t E = 2 * (M + 1), END = (E + 7u) & ~7u;
+    if (END + 1 >= 0xFFFFu) return 1;
+    const uint32_t SPEND = END >> 3, nSp = SPEND + 2, KW = (KS + 31) / 32;
+    uint32_t* Node = A.alloc<uint32_t>(E);
+    uint16_t* N16 = reinterpret_cast<uint16_t*>(Node);             // N16[2x] = successor of x, N16[2x + 1] = weight of x
     uint16_t* HV = A.alloc<uint16_t>(M + 1);
     uint16_t* Prun = A.alloc<uint16_t>(M + 1);
     uint16_t* VisBase = Prun;                                      // written at the very end, when the parent links are dead
     uint16_t* RKey = A.alloc<uint16_t>(M + 2);
     uint16_t* Last = RKey;
-    uint16_t* ByG = A.alloc<uint16_t>(M + 1);
-    const uint32_t uBytes = max(max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)(((nSp + 1) * 4 + 15) & ~15u)),
+    // ByG[pos] (run with the pos-th smallest head key) lives in the weight halves of the exit nodes until the tour is threaded
+    auto ByG = [&](uint32_t pos) -> uint16_t& { return N16[2 * ((M + 1) + pos) + 1]; };
+    const uint32_t uBytes = max(max((uint32_t)(((KW + 1) * 4 + 15) & ~15u) + (uint32_t)(((KW + 1) * 2 + 15) & ~15u), 2u * (uint32_t)((nSp * 4 + 15) & ~15u)),
                                 (uint32_t)(((M + 32) * 2 + 15) & ~15u));
     char* U = A.alloc<char>(uBytes);     // successively: key bitmap + prefix | per-warp run lists of the threading | splitter summaries
     if (!A.fits()) return 1;
     uint32_t* KBits = reinterpret_cast<uint32_t*>(U);
     uint16_t* KPre = reinterpret_cast<uint16_t*>(U + (((KW + 1) * 4 + 15) & ~15u));
     uint32_t* Sub = reinterpret_cast<uint32_t*>(U);
-    uint32_t* Sub2 = reinterpret_cast<uint32_t*>(U + (((nSp + 1) * 4 + 15) & ~15u));
+    uint32_t* Sub2 = reinterpret_cast<uint32_t*>(U + ((nSp * 4 + 15) & ~15u));
     for (uint32_t w = tid; w < NWr; w += NT) {
         const uint4 q = WI[w];
         uint32_t hb = q.y, rid = q.w & 0xFFFFu;
@@ -218,7 +221,7 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
         const uint32_t p = rec.y == 0 ? n : (uint32_t)T[keyOf(rec.y, rec.z >> 16)];
         const uint32_t q = p == n ? M : runOf(p);
         const uint32_t hv = visBefore(i);
-        Wt[r] = (uint16_t)(visBefore(end) - hv);
+        N16[2 * r + 1] = (uint16_t)(visBefore(end) - hv);
         Prun[r] = (uint16_t)q; RKey[r] = (uint16_t)key;
         atomicOr(&KBits[key >> 5], 1u << (key & 31));
         HV[r] = (uint16_t)hv;                                       // (each thread rewrites only its own entries)
@@ -237,7 +240,7 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
     __syncthreads();
     for (uint32_t r = tid; r < M; r += NT) {
         const uint32_t key = RKey[r];
-        ByG[(uint32_t)KPre[key >> 5] + __popc(KBits[key >> 5] & ((1u << (key & 31)) - 1u))] = (uint16_t)r;
+        ByG((uint32_t)KPre[key >> 5] + __popc(KBits[key >> 5] & ((1u << (key & 31)) - 1u))) = (uint16_t)r;
     }
     __syncthreads();
     for (uint32_t x = tid; x < M + 2; x += NT) Last[x] = (uint16_t)kNone16;      // RKey, KBits, KPre are dead from here
@@ -251,7 +254,7 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
         uint32_t mine = 0;
         for (uint32_t cb = 0; cb < M; cb += 32) {
             const uint32_t pos = cb + lane;
-            const bool ok = pos < M && ((uint32_t)Prun[ByG[pos]] % TEAM) == warp;
+            const bool ok = pos < M && ((uint32_t)Prun[ByG(pos)] % TEAM) == warp;
             mine += __popc(__ballot_sync(kFull, ok));
         }
         if (lane == 0) c.wa[warp] = mine;
@@ -262,7 +265,7 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
         uint32_t o = off;
         for (uint32_t cb = 0; cb < M; cb += 32) {
             const uint32_t pos = cb + lane;
-            const uint32_t r = pos < M ? (uint32_t)ByG[pos] : 0u;
+            const uint32_t r = pos < M ? (uint32_t)ByG(pos) : 0u;
             const bool ok = pos < M && ((uint32_t)Prun[r] % TEAM) == warp;
             const uint32_t bal = __ballot_sync(kFull, ok);
             if (ok) Lst[o + __popc(bal & lt)] = (uint16_t)r;
@@ -286,34 +289,32 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
             if (valid) ns = lower ? rs : (uint32_t)Last[q];
             __syncwarp();
             if (valid) {
-                Next[(M + 1) + r] = (uint16_t)(ns != kNone16 ? ns : (M + 1) + q);
+                N16[2 * ((M + 1) + r)] = (uint16_t)(ns != kNone16 ? ns : (M + 1) + q);   // exit(r): next sibling, else exit(parent); (other warps may still read ByG)
                 if (((mask >> lane) >> 1) == 0) Last[q] = (uint16_t)r;
             }
             __syncwarp();
         }
     }
     __syncthreads();
-    if (tid == 0) { Sub[SPEND] = SPEND; Sub2[SPEND] = SPEND; }
-    for (uint32_t r = tid; r <= M; r += NT) { const uint32_t f = Last[r]; Next[r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); }
-    if (tid == 0) { Wt[M] = 0; Next[(M + 1) + M] = (uint16_t)END; Next[END] = (uint16_t)END; }
+    for (uint32_t r = tid; r <= M; r += NT) { const uint32_t f = Last[r]; N16[2 * r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); if (r < M) N16[2 * ((M + 1) + r) + 1] = 0; }   // exits weigh 0 (ByG is dead)
+    if (tid == 0) { N16[2 * M + 1] = 0; Node[(M + 1) + M] = END; }
     __syncthreads();
     {
-        const uint32_t headNode = M;
-        auto spOf = [&](uint32_t x) -> uint32_t { return (x & 7u) == 0 ? (x >> 3) : nSp - 1; };
-        auto isSp = [&](uint32_t x) -> bool { return (x & 7u) == 0 || x == headNode; };
+        const uint32_t headNode = M;                               // (no node's successor is the tour's first node)
         for (uint32_t k = tid; k < nSp; k += NT) {
-            uint32_t cur = k + 1 < nSp ? 8 * k : headNode, acc = 0, nx = END;
-            const bool valid = cur < E && (k + 1 < nSp || (headNode & 7u) != 0);
+            uint32_t cur = k < SPEND ? 8 * k : headNode, acc = 0, nx = END;
+            const bool valid = k < SPEND ? cur < E : (k > SPEND && (headNode & 7u) != 0);
             if (valid) {
                 for (;;) {
-                    nx = Next[cur];
-                    Next[cur] = (uint16_t)k;
-                    if (cur <= M) { const uint32_t wv = Wt[cur]; Wt[cur] = (uint16_t)acc; acc += wv; }
-                    if (nx == END || isSp(nx)) break;
+                    const uint32_t a = Node[cur];
+                    nx = a & 0xFFFFu;
+                    Node[cur] = k | (acc << 16);                   // owner | weight prefix before this node
+                    acc += a >> 16;
+                    if ((nx & 7u) == 0) break;
                     cur = nx;
                 }
             }
-            Sub[k] = valid ? ((acc << 16) | (nx == END ? SPEND : spOf(nx))) : SPEND;
+            Sub[k] = (acc << 16) | (nx >> 3);                      // invalid / terminator entries: weight 0, successor SPEND
         }
         __syncthreads();
         uint32_t *cur = Sub, *nxt2 = Sub2;
@@ -326,7 +327,8 @@ __device__ int team_merge_one_log(const BatchParams& P, const uint32_t li, TeamC
             uint32_t* t = cur; cur = nxt2; nxt2 = t;
         }
         for (uint32_t r = tid; r < M; r += NT) {
-            const uint32_t suf = (cur[Next[r]] >> 16) - (uint32_t)Wt[r];
+            const uint32_t a = Node[r];
+            const uint32_t suf = (cur[a & 0xFFFFu] >> 16) - (a >> 16);
             VisBase[r] = (uint16_t)((nvis - suf) - (uint32_t)HV[r]);
         }
     }

@@ -408,7 +408,7 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
 #pragma unroll 1
         for (uint32_t rb = 0; rb <= M; rb += 32) {                 // enter(r): first child, else exit(r)
             const uint32_t r = rb + lane;
-            if (r <= M) { const uint32_t f = Last[r]; N16[2 * r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); N16[2 * ((M + 1) + r) + 1] = 0; }   // exits weigh 0 (ByG is dead)
+            if (r <= M) { const uint32_t f = Last[r]; N16[2 * r] = (uint16_t)(f != kNone16 ? f : (M + 1) + r); if (r < M) N16[2 * ((M + 1) + r) + 1] = 0; }   // exits weigh 0 (ByG is dead)
         }
         if (lane == 0) { N16[2 * M + 1] = 0; Node[(M + 1) + M] = END; }
         __syncwarp();
