@@ -54,7 +54,8 @@ struct BatchParams {
     uint32_t* retry_count;
     const uint32_t* n_work_dev;           // non-null: number of work items is read from device memory (retry launch)
     uint32_t prefetch_next;               // CTA-per-log kernel: prefetch the next log's records into L2 while working on the current one
-    uint32_t warp_flags;                  // warp-per-log kernel: bit0 prefetch this log's marks, bit1 the next log's records, bit2 phase-aligned warps
+    uint32_t warp_flags;                  // warp-per-log kernel (PT_WARP_FLAGS, default 0x704): bit0 prefetch this log's marks, bit1 the next round's
+                                          // records, bit2 round-aligned warps, bits 8-11 skip in-log phase barrier 2 / 3 / 4 / 5
     uint32_t use_tma;                     // stage the record stream through shared memory with cp.async.bulk (shared-only path)
     uint32_t* seq;                        // optional: element sequence output (record index | after-slot defined << 30 | deleted << 31), text offsets
     const uint32_t* admit;                // optional: per-log admission status (pre-pass); non-zero: the log is not merged

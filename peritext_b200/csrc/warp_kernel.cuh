@@ -868,8 +868,9 @@ __device__ __forceinline__ int warp_merge_one_log(const BatchParams& P, const ui
 
 // Persistent warps: every warp pulls logs (largest first) from the bin's work queue.  Two modes:
 //   free  : each warp takes kWarpGrab logs per atomic and runs on its own;
-//   phased: (warp_flags bit 2, the default) the CTA takes one log per warp per ROUND and its warps pass the phase barriers together
-//           (consecutive logs of the size-sorted queue are nearly the same size, so a round's warps finish together).
+//   phased: (warp_flags bit 2, the default) the CTA takes one log per warp per ROUND: its warps start a round together (consecutive
+//           logs of the size-sorted queue are nearly the same size, so they also finish together) and share the instruction caches;
+//           the named barriers at the phase boundaries INSIDE a log are optional (bits 8-11 skip them; default: only the last one).
 template <int WARPS, int IDM>
 __global__ void __launch_bounds__(WARPS * 32, (32 / WARPS) > 0 ? (32 / WARPS) : 1) merge_logs_warp_kernel(const BatchParams P) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
