@@ -14,6 +14,8 @@ Phases (same letters as peritext_b200/csrc/merge_kernel.cuh):
   G  marks           element-index intervals, boundary bitmap -> segments, stabbing-max per LWW type
   H  comments        per-id elementary pieces -> visible presence pieces -> head flags
   I  spans           head flags -> spans, comment lists, digest
+form="visible" swaps G-I for the warp kernel's cut (peritext_b200/csrc/warp_kernel.cuh): intervals in visible space, ops that
+cover no visible element dropped, marks evaluated per visible position (`spans_visible_form`).
 """
 from __future__ import annotations
 
@@ -43,8 +45,49 @@ EMPTY = -1
 ROOT = -2
 
 
-def merge_log(ins, mk, n_actors, max_ctr):
-    """Returns dict(status, n_elems, n_visible, tokens, spans=[(start, flags, link, (comment ids...))], digest)."""
+def spans_visible_form(mk, iv, vis_rank, nvis, mark_keys):
+    """Phases G-I the way the WARP kernel computes them (peritext_b200/csrc/warp_kernel.cuh): mark intervals are mapped to
+    VISIBLE space, ops that cover no visible element are dropped, and marks / link / comment-id set are evaluated per
+    visible position; a span starts where any of them differs from the position before.  (The kernel's segment form
+    evaluates the same thing once per elementary segment of the survivors' boundaries.)"""
+    surv = []                                  # (va, vb, op index)
+    for k, x in enumerate(iv):
+        if x:
+            va, vb = vis_rank[x[0]], vis_rank[x[1]]
+            if va < vb:
+                surv.append((va, vb, k))
+    per_pos = []
+    for x in range(nvis):
+        cover = [k for (va, vb, k) in surv if va <= x < vb]
+        flags, link = 0, ATTR_NONE
+        for t, bit in ((0, 1), (1, 2), (3, 4)):
+            ops = [k for k in cover if ((int(mk[k]["kind"]) >> 1) & 3) == t]
+            if ops:
+                w = max(ops, key=lambda k: mark_keys[k])            # LWW by opId (peritext.ts:304-313)
+                if (int(mk[w]["kind"]) & 1) == 0:
+                    flags |= bit
+                    if t == 3:
+                        link = int(mk[w]["attr"])
+        cops = [k for k in cover if ((int(mk[k]["kind"]) >> 1) & 3) == 2]
+        if cops:
+            flags |= 8                                              # quirk Q3: the key exists as soon as any comment op covers
+        ids = set()
+        for cid in set(int(mk[k]["attr"]) for k in cops):
+            last = max(k for k in cops if int(mk[k]["attr"]) == cid)    # arrival order (quirk Q4)
+            if (int(mk[last]["kind"]) & 1) == 0:
+                ids.add(cid)
+        per_pos.append((flags, link, tuple(sorted(ids))))
+    spans = []
+    for x in range(nvis):
+        if x == 0 or per_pos[x] != per_pos[x - 1]:
+            fl, ln, cl = per_pos[x]
+            spans.append((x, fl | (len(cl) << 8), ln, cl))
+    return spans
+
+
+def merge_log(ins, mk, n_actors, max_ctr, form="element"):
+    """Returns dict(status, n_elems, n_visible, tokens, spans=[(start, flags, link, (comment ids...))], digest).
+    form: "element" = phases G-I in element space as the CTA kernel does them; "visible" = as the warp kernel does them."""
     n, m, R = len(ins), len(mk), int(n_actors)
     C = int(max_ctr)
     out = dict(status=0, n_elems=0, n_visible=0, tokens=[], spans=[], digest=(0, 0))
@@ -305,6 +348,8 @@ def merge_log(ins, mk, n_actors, max_ctr):
         cl = sorted(cid for (cid, va, vb) in pieces if va <= v < vb)
         flags = seg_flags[s] | (len(cl) << 8)
         spans.append((v, flags, seg_link[s], tuple(cl)))
+    if form == "visible":
+        spans = spans_visible_form(mk, iv, vis_rank, nvis, mark_keys)
     d0 = d1 = 0
 
     def add(t):
@@ -322,7 +367,7 @@ def merge_log(ins, mk, n_actors, max_ctr):
     return out
 
 
-def merge_batch(batch: PackedBatch) -> MergedBatch:
+def merge_batch(batch: PackedBatch, form="element") -> MergedBatch:
     desc = batch.desc
     text_off, span_off, n_text, n_span = output_layout(desc)
     results = np.zeros(len(desc), RESULT_DT)
@@ -331,7 +376,7 @@ def merge_batch(batch: PackedBatch) -> MergedBatch:
     pool = []
     for i in range(len(desc)):
         ins, mk = batch.log_slice(i)
-        o = merge_log(ins, mk, desc[i]["n_actors"], desc[i]["max_ctr"])
+        o = merge_log(ins, mk, desc[i]["n_actors"], desc[i]["max_ctr"], form=form)
         results[i]["status"] = o["status"]
         if o["status"]:
             continue

@@ -13,11 +13,13 @@ from tests.harness import fuzz_session, generateDocs, load_kats, run_concurrent
 def check_equal(logs, expect_spans=None):
     b = pack_logs(logs)
     ref, _ = replay_packed(b)
-    got = kernel_model.merge_batch(b)
-    for i in range(b.n_logs):
-        assert got.canonical(i) == ref.canonical(i), f"log {i}"
-        if expect_spans is not None:
-            assert decode_spans(b, got, i) == expect_spans[i]
+    # both cuts of the mark overlay: element space (CTA kernel) and visible space (warp kernel)
+    for form in ("visible", "element"):
+        got = kernel_model.merge_batch(b, form=form)
+        for i in range(b.n_logs):
+            assert got.canonical(i) == ref.canonical(i), f"log {i} ({form} form)"
+            if expect_spans is not None:
+                assert decode_spans(b, got, i) == expect_spans[i]
     return b, got
 
 
